@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- grid-cell-updates/s of the SOR sweep on B200 (+ CPU reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c1|c5] [--sweeps M] [--engine auto|colour|fused]
+
+A *step* is one pass of the hot path over one batch of synthetic input: M SOR
+sweeps (default 1000 = the reference notebook's mxLoop for the global-ocean
+case) of the BASELINE.json configs[1] problem -- invert_Poisson on a 3600x1800
+global lat-lon grid with a ~20 % land mask, extend/periodic BCs -- one such
+slice per GPU (north star: slices sharded one-per-GPU, weak scaling).  The
+tolerance is set to -1 (never met; the reference's own fixed-sweep trick,
+tests/test_GeoAdjustment.py:31) so every step does identical work; the stop
+test (mean|S| reduction + decide) still runs every sweep inside the timed region.
+
+value  = cell-updates/s with operands resident in HBM when the timed region starts;
+e2e    = same through the C-ABI with HOST (pinned) buffers: H2D of S,A,C,F and
+         D2H of S inside the timed region, every step.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "grid-cell-updates/sec (SOR sweep)"
+UNIT = "cell-updates/s"
+UNDEF = -9.99e8
+
+WORKLOADS = {
+    # name: (ny, nx, slices per GPU, BCs, description)
+    "c2": (1800, 3600, 1, ("extend", "periodic"),
+           "configs[1]: invert_Poisson 3600x1800 global lat-lon, ~20% land mask, extend/periodic, omega=auto"),
+    "c1": (180, 360, 1, ("fixed", "periodic"),
+           "configs[0]: invert_Poisson 360x180 lat-lon, periodic-x, omega=1.4"),
+    "c5": (720, 1440, 32, ("fixed", "periodic"),
+           "configs[4]: batched invert_Poisson 1440x720, 32 time slices per GPU"),
+}
+
+
+def env_rank():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def make_problem(name, rank, pinned=False):
+    """Synthetic operands of one rank's shard (SURVEY.md 8d recipes)."""
+    from tests import cases
+    import xinvert_b200 as xb
+    ny, nx, per_gpu, bcs, _ = WORKLOADS[name]
+    c = cases.poisson_latlon(ny, nx, land=(name != "c1"), noise=1e-6, seed=1000 + rank,
+                             batch=per_gpu if per_gpu > 1 else None, phase=0.37 * rank)
+    if name == "c1":
+        c["p"]["optArg"] = 1.4
+    if pinned:
+        for k in ("A", "C", "F", "S0"):
+            buf = xb.pinned_empty(c[k].shape)
+            buf[...] = c[k]
+            c[k] = buf
+    return c, bcs
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc = gpu_index, None
+        self.path = tempfile.mktemp(prefix="xinv_clocks_", suffix=".csv")
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for nme, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------
+def cpu_reference_rate(name, sweeps, rank=0):
+    """Reference algorithm (lexicographic SOR, numbas.py:215-416) through the C
+    oracle port on ONE host thread -- the reference is single-threaded by
+    construction and one slice cannot use more."""
+    import oracle
+    from tests import cases
+    c, bcs = make_problem(name, rank)
+    p = c["p"]
+    S0 = c["S0"] if c["S0"].ndim == 2 else c["S0"][0]
+    F = c["F"] if c["F"].ndim == 2 else c["F"][0]
+    cc = dict(A=c["A"], C=c["C"], F=F, S0=S0, p=p)
+    cases.run_std2d(oracle, dict(cc, S0=S0.copy()), bcs[0], bcs[1], 0, -1.0)       # warm caches / page in
+    t0 = time.perf_counter()
+    _, fl = cases.run_std2d(oracle, cc, bcs[0], bcs[1], sweeps - 1, -1.0)
+    dt = time.perf_counter() - t0
+    assert int(fl[2]) + 1 == sweeps
+    return sweeps * S0.size / dt, dt
+
+
+def run_reference(args):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    ny, nx, per_gpu, bcs, desc = WORKLOADS[args.workload]
+    sweeps = args.ref_sweeps or max(2, int(round(2.0e8 / (ny * nx))))          # ~2-3 s of CPU per step
+    for _ in range(args.warmup):
+        cpu_reference_rate(args.workload, max(2, sweeps // 8))
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt = cpu_reference_rate(args.workload, sweeps)
+        rates.append(r); times.append(dt)
+    value = sweeps * ny * nx * args.steps / sum(times)
+    sample = f"{sweeps} lexicographic sweeps of one {nx}x{ny} slice per step, C port of numbas.py (gcc -O2, no FMA)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    rank, local_rank, world = env_rank()
+    import torch
+    import xinvert_b200 as xb
+    from xinvert_b200 import distributed as xd
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (xinvert_b200 has no CPU fallback)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    ctx = xb.Context(local_rank)
+    allreduce = None
+    if world > 1:
+        allreduce = xd.XinvNcclAllReduce(ctx, rank, world) if args.collective == "xinv-nccl" else xd.TorchAllReduce()
+
+    ny, nx, per_gpu, bcs, desc = WORKLOADS[args.workload]
+    c, _ = make_problem(args.workload, rank, pinned=True)
+    p = c["p"]
+    N = ny * nx
+    sweeps = args.sweeps
+    kw = dict(undef=UNDEF, mxLoop=sweeps - 1, tolerance=-1.0, ctx=ctx, engine=args.engine)
+    pos = (bcs[0], bcs[1], p["del1Sqr"], p["ratioQtr"], p["ratioSqr"], p["optArg"])
+
+    # ---- device-resident operands (value) --------------------------------
+    dA, dC, dF = (torch.from_numpy(np.ascontiguousarray(c[k])).to(dev) for k in ("A", "C", "F"))
+    dS0 = torch.from_numpy(np.ascontiguousarray(c["S0"])).to(dev)
+    dS = dS0.clone()
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(profile=False):
+        dS.copy_(dS0)
+        torch.cuda.synchronize()          # torch stream -> library stream hand-over (a 52 MB memset-like copy)
+        return xd.solve_standard_2D_sharded(dS, dA, None, dC, dF, *pos, allreduce=allreduce, profile=profile, **kw)
+
+    def step_host():
+        S = hS
+        S[...] = c["S0"]
+        return xd.solve_standard_2D_sharded(S, c["A"], None, c["C"], c["F"], *pos, allreduce=allreduce, **kw)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches = 0
+    solve_ms = 0.0
+    dom_ms, dom_n = 0.0, 0
+    t0 = time.perf_counter()
+    ctx.timer_start()                          # CUDA events on the library's stream bracket the K steps
+    for _ in range(args.steps):
+        fl, st, _ = step_device(profile=True)
+        launches += st["kernel_launches"]
+        solve_ms += st["solve_ms"]
+        dom_ms += st["dom_ms"]; dom_n += st["dom_launches"]
+    ev_s = ctx.timer_stop() / 1e3
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+    assert int(fl[0, 2]) + 1 == sweeps, (fl[0], sweeps)
+    engine_used, ncol = st["engine"], st["ncolours"]
+
+    # ---- end to end through the C-ABI with host buffers ---------------------
+    hS = xb.pinned_empty(c["S0"].shape)
+    step_host()
+    barrier()
+    t1 = time.perf_counter()
+    ctx.timer_start()
+    h2d = d2h = 0
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        _, st_h, _ = step_host()
+        h2d, d2h = st_h["h2d_bytes"], st_h["d2h_bytes"]
+    ev_e2e = ctx.timer_stop() / 1e3
+    barrier()
+    wall_e2e = time.perf_counter() - t1
+
+    # ---- reduce over ranks: device time of the timed region = max over ranks ----
+    t_dev = solve_ms / 1e3
+    vals = torch.tensor([t_dev, wall, wall_e2e, ev_s, ev_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    t_dev, wall, wall_e2e, ev_s, ev_e2e = (float(v) for v in vals.tolist())
+    tot_launch = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tot_launch)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    units_per_step = sweeps * N * per_gpu * world
+    value = units_per_step * args.steps / ev_s             # CUDA-event time, max over ranks
+    e2e_value = units_per_step * e2e_steps / ev_e2e
+
+    # ---- roofline of the dominant kernel (SURVEY.md 8d algorithmic bytes) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
+    if engine_used == "fused":
+        alg_bytes = 40.0 * N * per_gpu          # one fused red+black iteration: S r+w, A, C, F once
+        kern = "fused red+black iteration kernel"
+    else:
+        alg_bytes = 32.0 * N * per_gpu          # one colour sweep: S 8N r + 4N w, A 8N, C 8N, F 4N
+        kern = "colour sweep kernel (one launch per colour)"
+    achieved = (alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9) if dom_n else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "kernel": kern, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "avg_launch_us": (dom_ms / dom_n * 1e3) if dom_n else None, "timed_launches": dom_n}
+
+    # ---- CPU baseline: bounded sample of the same workload on one host core ----
+    cpu_sweeps = args.cpu_sweeps or max(2, int(round(1.2e9 / N)))             # ~10-20 s of CPU work
+    cpu_rate, cpu_dt = cpu_reference_rate(args.workload, cpu_sweeps)
+    cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
+                    "sample": f"{cpu_sweeps} lexicographic sweeps of one {nx}x{ny} slice ({cpu_dt:.1f} s), "
+                              "C port of numbas.py, 1 thread (the reference is single-threaded)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "sweeps_per_step": sweeps,
+                   "slices_per_gpu": per_gpu, "grid": [ny, nx], "engine": engine_used, "colours": ncol,
+                   "ordering": "red-black", "l2": f"operands {5 * 8 * N * per_gpu / 1e6:.0f} MB per GPU "
+                   + ("> 126 MB L2 (no flush needed)" if 40 * N * per_gpu > 126e6 else "< L2: L2-resident workload"),
+                   "collective": (args.collective if world > 1 else "none"),
+                   "sweep_loop_ms_per_step": 1e3 * t_dev / args.steps,
+                   "wall_ms_per_step": 1e3 * wall / args.steps},
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "ms_per_step": 1e3 * ev_e2e / e2e_steps},
+        "gpu_launches": int(tot_launch.item()), "clocks": clk,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--sweeps", type=int, default=1000, help="SOR sweeps per step (GPU arm)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "colour", "fused"])
+    ap.add_argument("--collective", default="xinv-nccl", choices=["xinv-nccl", "torch"])
+    ap.add_argument("--cpu-sweeps", type=int, default=0, help="sweeps of the cpu_baseline sample (0 = ~10-20 s)")
+    ap.add_argument("--ref-sweeps", type=int, default=0, help="sweeps per step of --impl reference (0 = ~2-3 s)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

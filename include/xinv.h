@@ -1,0 +1,195 @@
+/*
+ * xinv.h -- C-ABI of libxinv_b200.so: the B200-native SOR elliptic inverter.
+ *
+ * Drop-in boundary: these entry points replace the call
+ *     core.inv_*  ->  numbas.invert_*
+ * of the reference (/root/reference/xinvert/core.py:130-139, :419-428, :60-69),
+ * batched over all non-core slices (the serial `for selDict in loop_noncore`
+ * loop of core.py:129/418/59 becomes the `batch` argument).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types.
+ *   - all arrays are C-contiguous float64, x fastest: [batch][ny][nx] or
+ *     [batch][nz][ny][nx].  S is in/out (warm start: the solve continues from
+ *     whatever S holds, as numbas.py does); coefficients / forcing are read-only.
+ *   - `flags` is a HOST array double[batch][3] = (overflow 0/1, last relative
+ *     change of mean|S|, last loop index), the per-slice equivalent of the
+ *     reference's flags[3] (numbas.py:403-408).  It is read on entry (values a
+ *     slice keeps when it overflows in its first sweep) and written on return.
+ *   - return value: 0 = ok, <0 = error (XINV_E_*); xinv_last_error() gives the
+ *     text.  Numerical blow-up is NOT an error: it sets flags[b][0] = 1 and
+ *     stops that slice, exactly like numbas.py:403-405.
+ *   - pointers are borrowed for the duration of the call only.
+ *   - one xinv_ctx per (thread, device); calls on one ctx are stream-ordered
+ *     and must not be issued concurrently from several threads.
+ */
+#ifndef XINV_H
+#define XINV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XINV_VERSION 100
+
+/* boundary conditions (numbas.py BCy/BCx strings 'fixed' / 'extend' / 'periodic') */
+#define XINV_BC_FIXED    0
+#define XINV_BC_EXTEND   1
+#define XINV_BC_PERIODIC 2
+
+/* orderings */
+#define XINV_ORDER_COLOUR 0   /* red-black (5/7-pt) or 4-colour (9-pt): the fast path   */
+#define XINV_ORDER_LEX    1   /* reference's lexicographic order, wavefront-parallel:   */
+                              /* bit-identical trajectory to numbas.py, slower          */
+
+/* where S / coefficient / forcing pointers live */
+#define XINV_MEM_HOST   0     /* library stages H2D / D2H itself                        */
+#define XINV_MEM_DEVICE 1     /* device pointers on ctx's device (e.g. tensor.data_ptr) */
+
+/* engines (opts.engine); 0 lets the library choose */
+#define XINV_ENGINE_AUTO    0
+#define XINV_ENGINE_COLOUR  1 /* one in-place kernel per colour + fused norm/decide     */
+#define XINV_ENGINE_FUSED   2 /* TMA-staged fused red+black iteration kernel (2-D, B==0)*/
+
+/* error codes */
+#define XINV_OK          0
+#define XINV_E_ARG      -1    /* bad argument                                           */
+#define XINV_E_CUDA     -2    /* CUDA runtime / driver error                            */
+#define XINV_E_STATE    -3    /* begin/step/end protocol violated                       */
+#define XINV_E_NOMEM    -4
+#define XINV_E_UNSUPPORTED -5 /* e.g. lexicographic ordering with periodic-x 9-point    */
+#define XINV_E_NCCL     -6
+
+typedef struct xinv_ctx xinv_ctx;
+
+/* Options; pass NULL for defaults (host pointers, colour ordering, dense
+ * coefficients, automatic engine and check interval). */
+typedef struct xinv_opts {
+    int32_t struct_size;      /* = sizeof(xinv_opts)                                    */
+    int32_t ordering;         /* XINV_ORDER_*                                           */
+    int32_t mem_space;        /* XINV_MEM_*                                             */
+    int32_t engine;           /* XINV_ENGINE_*                                          */
+    int32_t check_every;      /* sweeps between host polls of the active count; 0=auto  */
+    int32_t profile;          /* 1: time the dominant (sweep) kernels with CUDA events   */
+    /* batch stride (in elements) of each coefficient/forcing array, in argument
+     * order (A,B,C,F | A..G | A,B,C,F).  -1 = dense (one slice per batch entry,
+     * as the reference materialises them); 0 = one slice shared by the whole
+     * batch (what xarray broadcasting of time-independent coefficients means). */
+    int64_t coef_stride[8];
+} xinv_opts;
+
+/* Statistics of the last solve on a ctx. */
+typedef struct xinv_stats {
+    int64_t sweeps_launched;  /* iterations launched (>= max_b(flags[b][2]+1))          */
+    int64_t kernel_launches;  /* kernels of this library launched                        */
+    int64_t cell_updates;     /* sum_b (flags[b][2]+1) * cells-of-slice                  */
+    double  solve_ms;         /* device time of the iteration loop (CUDA events)         */
+    double  h2d_ms, d2h_ms;   /* staging time when mem_space == HOST                     */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t engine;           /* engine that ran                                         */
+    int32_t ncolours;
+    double  sweep_ms;         /* mean device time of one full sweep (all colours)        */
+    double  dom_ms;           /* opts.profile: summed device time of the dominant kernels */
+    int64_t dom_launches;     /*               ... and how many launches that covers      */
+} xinv_stats;
+
+/* ---- context ---------------------------------------------------------- */
+int  xinv_create(xinv_ctx **out, int device);
+/* same, but work is issued on the caller's cudaStream_t (e.g. torch's current stream) */
+int  xinv_create_on_stream(xinv_ctx **out, int device, void *cuda_stream);
+void xinv_destroy(xinv_ctx *ctx);
+const char *xinv_last_error(void);
+int  xinv_version(void);
+int  xinv_get_stats(const xinv_ctx *ctx, xinv_stats *out);
+int  xinv_device_count(int *out);
+int  xinv_synchronize(xinv_ctx *ctx);
+/* CUDA-event stopwatch on the ctx's stream (what bench.py brackets its timed region with) */
+int  xinv_timer_start(xinv_ctx *ctx);
+int  xinv_timer_stop(xinv_ctx *ctx, double *ms_out);   /* records, synchronises, returns ms */
+
+/* pinned host memory helpers (so callers can stage at full PCIe rate) */
+int  xinv_host_alloc(void **out, int64_t bytes);
+int  xinv_host_free(void *p);
+/* device memory helpers for callers without torch (bench / tests) */
+int  xinv_dev_alloc(xinv_ctx *ctx, void **out, int64_t bytes);
+int  xinv_dev_free(xinv_ctx *ctx, void *p);
+int  xinv_memcpy_h2d(xinv_ctx *ctx, void *dst, const void *src, int64_t bytes);
+int  xinv_memcpy_d2h(xinv_ctx *ctx, void *dst, const void *src, int64_t bytes);
+
+/* ---- one-call solvers -------------------------------------------------- */
+
+/* Replaces core.inv_standard2D -> numbas.invert_standard_2D
+ * (core.py:129-139, numbas.py:215-416).  B == NULL means B is identically 0
+ * (5-point stencil, red-black); otherwise the 9-point stencil with a 4-colour
+ * ordering is used. */
+int xinv_std2d(xinv_ctx *ctx, double *S, const double *A, const double *B,
+               const double *C, const double *F,
+               int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+               double delxSqr, double ratioQtr, double ratioSqr,
+               double optArg, double undef, double *flags,
+               int64_t mxLoop, double tolerance, const xinv_opts *opts);
+
+/* Replaces core.inv_general2D -> numbas.invert_general_2D
+ * (core.py:418-428, numbas.py:987-1201).  B == NULL means B == 0. */
+int xinv_gen2d(xinv_ctx *ctx, double *S, const double *A, const double *B,
+               const double *C, const double *D, const double *E,
+               const double *F, const double *G,
+               int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+               double delx, double delxSqr, double ratio, double ratioQtr,
+               double ratioSqr, double optArg, double undef, double *flags,
+               int64_t mxLoop, double tolerance, const xinv_opts *opts);
+
+/* Replaces core.inv_standard3D -> numbas.invert_standard_3D
+ * (core.py:59-69, numbas.py:15-212).  bcz is accepted and ignored, as in the
+ * reference (numbas.py never reads BCz). */
+int xinv_std3d(xinv_ctx *ctx, double *S, const double *A, const double *B,
+               const double *C, const double *F,
+               int64_t batch, int64_t nz, int64_t ny, int64_t nx,
+               int bcz, int bcy, int bcx,
+               double delxSqr, double ratio2Sqr, double ratio1Sqr,
+               double optArg, double undef, double *flags,
+               int64_t mxLoop, double tolerance, const xinv_opts *opts);
+
+/* ---- stepwise protocol (used by the multi-GPU driver so that ranks can
+ *      exchange their active-slice counts between chunks of sweeps) ---------
+ * xinv_*_begin stages the problem and initialises per-slice loop state;
+ * xinv_step runs up to `sweeps` more iterations and returns how many slices of
+ * this ctx are still active; xinv_end writes S / flags back and releases the
+ * problem.  xinv_std2d(...) == begin + step-until-0 + end. */
+int xinv_std2d_begin(xinv_ctx *ctx, double *S, const double *A, const double *B,
+                     const double *C, const double *F,
+                     int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                     double delxSqr, double ratioQtr, double ratioSqr,
+                     double optArg, double undef, double *flags,
+                     int64_t mxLoop, double tolerance, const xinv_opts *opts);
+int xinv_gen2d_begin(xinv_ctx *ctx, double *S, const double *A, const double *B,
+                     const double *C, const double *D, const double *E,
+                     const double *F, const double *G,
+                     int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                     double delx, double delxSqr, double ratio, double ratioQtr,
+                     double ratioSqr, double optArg, double undef, double *flags,
+                     int64_t mxLoop, double tolerance, const xinv_opts *opts);
+int xinv_std3d_begin(xinv_ctx *ctx, double *S, const double *A, const double *B,
+                     const double *C, const double *F,
+                     int64_t batch, int64_t nz, int64_t ny, int64_t nx,
+                     int bcz, int bcy, int bcx,
+                     double delxSqr, double ratio2Sqr, double ratio1Sqr,
+                     double optArg, double undef, double *flags,
+                     int64_t mxLoop, double tolerance, const xinv_opts *opts);
+int xinv_step(xinv_ctx *ctx, int64_t sweeps, int64_t *n_active_out);
+int xinv_end(xinv_ctx *ctx);
+
+/* ---- multi-GPU: scalar all-reduce of the active-slice count over NCCL ----
+ * (SURVEY.md 8e).  The unique id is created on rank 0 and distributed by the
+ * caller (torch.distributed broadcast, MPI, a file ...). */
+int xinv_nccl_unique_id(void *id128);                 /* writes 128 bytes */
+int xinv_nccl_init(xinv_ctx *ctx, const void *id128, int rank, int world);
+int xinv_nccl_allreduce_active(xinv_ctx *ctx, int64_t local, int64_t *global_out);
+int xinv_nccl_finalize(xinv_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XINV_H */

@@ -1,0 +1,7 @@
+"""xinvert_b200 -- B200-native (sm_100a) SOR elliptic inverter behind the
+xinvert API.  See DESIGN.md; the C-ABI is in include/xinv.h."""
+__version__ = "0.1.0"
+
+from ._lib import Context, XinvError, default_context, device_count, pinned_empty  # noqa: F401
+from .solvers import (invert_general_2D, invert_standard_2D, invert_standard_3D,  # noqa: F401
+                      solve_general_2D, solve_standard_2D, solve_standard_3D)

@@ -1,0 +1,219 @@
+"""ctypes binding of ``libxinv_b200.so`` (the C-ABI in ``include/xinv.h``).
+
+There is no CPU fallback: if the shared library is missing it is built with
+nvcc; if that fails, or if no B200 is visible when a solve is requested, the
+call raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import build as _build
+
+BC_CODES = {"fixed": 0, "extend": 1, "periodic": 2}
+ORDER_CODES = {"colour": 0, "color": 0, "redblack": 0, "red-black": 0,
+               "lexicographic": 1, "lex": 1}
+ENGINE_CODES = {"auto": 0, "colour": 1, "color": 1, "fused": 2}
+ENGINE_NAMES = {0: "auto", 1: "colour", 2: "fused"}
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+class XinvOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("ordering", C.c_int32),
+                ("mem_space", C.c_int32), ("engine", C.c_int32),
+                ("check_every", C.c_int32), ("profile", C.c_int32),
+                ("coef_stride", C.c_int64 * 8)]
+
+
+class XinvStats(C.Structure):
+    _fields_ = [("sweeps_launched", C.c_int64), ("kernel_launches", C.c_int64),
+                ("cell_updates", C.c_int64), ("solve_ms", C.c_double),
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("engine", C.c_int32), ("ncolours", C.c_int32),
+                ("sweep_ms", C.c_double), ("dom_ms", C.c_double),
+                ("dom_launches", C.c_int64)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["engine"] = ENGINE_NAMES.get(d["engine"], d["engine"])
+        return d
+
+
+# every symbol include/xinv.h declares: (name, restype, argtypes)
+_vp, _i64, _dbl, _int = C.c_void_p, C.c_int64, C.c_double, C.c_int
+_P = C.POINTER
+_STD2D = [_vp] * 6 + [_i64, _i64, _i64, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
+_GEN2D = [_vp] * 9 + [_i64, _i64, _i64, _int, _int] + [_dbl] * 7 + [_vp, _i64, _dbl, _P(XinvOpts)]
+_STD3D = [_vp] * 6 + [_i64, _i64, _i64, _i64, _int, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
+SYMBOLS = [
+    ("xinv_create", _int, [_P(_vp), _int]),
+    ("xinv_create_on_stream", _int, [_P(_vp), _int, _vp]),
+    ("xinv_destroy", None, [_vp]),
+    ("xinv_last_error", C.c_char_p, []),
+    ("xinv_version", _int, []),
+    ("xinv_get_stats", _int, [_vp, _P(XinvStats)]),
+    ("xinv_device_count", _int, [_P(_int)]),
+    ("xinv_synchronize", _int, [_vp]),
+    ("xinv_timer_start", _int, [_vp]),
+    ("xinv_timer_stop", _int, [_vp, _P(_dbl)]),
+    ("xinv_host_alloc", _int, [_P(_vp), _i64]),
+    ("xinv_host_free", _int, [_vp]),
+    ("xinv_dev_alloc", _int, [_vp, _P(_vp), _i64]),
+    ("xinv_dev_free", _int, [_vp, _vp]),
+    ("xinv_memcpy_h2d", _int, [_vp, _vp, _vp, _i64]),
+    ("xinv_memcpy_d2h", _int, [_vp, _vp, _vp, _i64]),
+    ("xinv_std2d", _int, _STD2D),
+    ("xinv_gen2d", _int, _GEN2D),
+    ("xinv_std3d", _int, _STD3D),
+    ("xinv_std2d_begin", _int, _STD2D),
+    ("xinv_gen2d_begin", _int, _GEN2D),
+    ("xinv_std3d_begin", _int, _STD3D),
+    ("xinv_step", _int, [_vp, _i64, _P(_i64)]),
+    ("xinv_end", _int, [_vp]),
+    ("xinv_nccl_unique_id", _int, [_vp]),
+    ("xinv_nccl_init", _int, [_vp, _vp, _int, _int]),
+    ("xinv_nccl_allreduce_active", _int, [_vp, _i64, _P(_i64)]),
+    ("xinv_nccl_finalize", _int, [_vp]),
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class XinvError(RuntimeError):
+    """A negative return code of the C-ABI (argument, CUDA or NCCL error)."""
+
+
+def load():
+    """dlopen libxinv_b200.so (building it first if needed) and bind symbols."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            path = _build.build()
+            L = C.CDLL(path)
+            for name, res, args in SYMBOLS:
+                f = getattr(L, name)          # AttributeError if the symbol is missing
+                f.restype = res
+                f.argtypes = args
+            _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().xinv_last_error()
+        raise XinvError(f"libxinv_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = load().xinv_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+class Context:
+    """One ``xinv_ctx``: a device, a stream and reusable staging buffers."""
+
+    def __init__(self, device=0, stream=None):
+        L = load()
+        h = _vp()
+        if stream is None:
+            check(L.xinv_create(C.byref(h), int(device)))
+        else:
+            check(L.xinv_create_on_stream(C.byref(h), int(device), _vp(int(stream))))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().xinv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise XinvError("context is closed")
+        return self._h
+
+    def stats(self):
+        s = XinvStats()
+        check(load().xinv_get_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def synchronize(self):
+        check(load().xinv_synchronize(self.handle))
+
+    def timer_start(self):
+        check(load().xinv_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        check(load().xinv_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    """Process-wide context per device (created on first use)."""
+    ctx = _default_ctx.get(device)
+    if ctx is None or not ctx._h:
+        if device_count() <= device:
+            raise XinvError(
+                f"no CUDA device {device} visible: xinvert_b200 has no CPU fallback "
+                "(the SOR path runs only as sm_100a CUDA)")
+        ctx = Context(device)
+        _default_ctx[device] = ctx
+    return ctx
+
+
+def make_opts(ordering="colour", mem_space=MEM_HOST, engine="auto", check_every=0,
+              coef_strides=None, profile=False):
+    o = XinvOpts()
+    o.struct_size = C.sizeof(XinvOpts)
+    o.ordering = ORDER_CODES[ordering]
+    o.mem_space = mem_space
+    o.engine = ENGINE_CODES[engine]
+    o.check_every = int(check_every)
+    o.profile = 1 if profile else 0
+    for m in range(8):
+        o.coef_stride[m] = -1
+    if coef_strides:
+        for m, s in enumerate(coef_strides):
+            o.coef_stride[m] = int(s)
+    return o
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; numpy views keep it alive via .base."""
+
+    def __init__(self, nbytes):
+        p = _vp()
+        check(load().xinv_host_alloc(C.byref(p), int(nbytes)))
+        self.ptr = p.value
+        self.__array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                    "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.xinv_host_free(_vp(self.ptr))
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over cudaHostAlloc'ed (page-locked) memory."""
+    dtype = np.dtype(dtype)
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    n = int(np.prod(shape)) * dtype.itemsize
+    block = _PinnedBlock(max(n, 16))
+    return np.asarray(block)[:n].view(dtype).reshape(shape)

@@ -1,0 +1,58 @@
+"""Build libxinv_b200.so (hand-written sm_100a CUDA + the C-ABI) in-tree.
+
+    python -m xinvert_b200.build            # build if stale
+    python -m xinvert_b200.build --force
+
+nvcc cross-compiles without a GPU.  Flags that matter:
+  -gencode arch=compute_100a,code=sm_100a   B200 only; no other targets, no PTX JIT
+  -fmad=false     no FMA contraction: every +,-,*,/ is one IEEE binary64 op in
+                  the reference's evaluation order (numba fastmath=False), which
+                  is what makes bit-exact parity with the oracle possible.  The
+                  kernels are HBM-bound, so this costs nothing measurable.
+  -lineinfo       ncu source-page mapping
+  -cudart static  the .so loads (dlopen) on machines without a GPU or libcuda
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libxinv_b200.so")
+SOURCES = ["xinv_api.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+    "-Xcompiler", "-fPIC",
+    "-shared", "-cudart", "static",
+]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(HERE, "..", "include", "xinv.h"))
+    deps.append(os.path.abspath(__file__))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile the library if it is missing or older than its sources."""
+    if not force and not _stale():
+        return LIB
+    cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
+           *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB, "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libxinv_b200.so:\n" + r.stderr[-4000:])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

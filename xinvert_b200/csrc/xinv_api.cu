@@ -1,0 +1,826 @@
+// xinv_api.cu -- host side of libxinv_b200.so: context, staging, the sweep
+// driver (chunks of sweeps between host polls of the device-side active count)
+// and the extern "C" entry points declared in include/xinv.h.
+//
+// The reference's per-slice Python loop (core.py:129-153) and the iteration
+// loop of numbas.py:282-414 are replaced by: all slices resident in HBM, every
+// sweep a batched kernel launch over all still-active slices, per-slice loop
+// state (normPrev, loop, flags) updated on the device by the norm/decide
+// kernel, and the host only polling "how many slices are still active".
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <dlfcn.h>
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/xinv.h"
+#include "xinv_device.cuh"
+#include "xinv_colour_engine.cuh"
+#include "xinv_fused2d.cuh"
+#include "xinv_lex_engine.cuh"
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                   \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess)                                                     \
+            return set_err(XINV_E_CUDA, "%s failed: %s (%s:%d)", #call,            \
+                           cudaGetErrorString(e_), __FILE__, __LINE__);            \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct Problem {
+    bool open = false;
+    int kind = 0;
+    bool hasB = false;
+    int zero_exit = 0;
+    i64 batch = 0;
+    XdGeom g{};
+    XdCoef q{};
+    double *dS = nullptr;        // device S [batch][N]
+    double *dS2 = nullptr;       // ping-pong partner (fused engine)
+    double *userS = nullptr;     // caller's S (host or device)
+    double *userFlags = nullptr; // host flags [batch][3]
+    int mem_space = 0;
+    int ordering = 0;
+    int engine = 0;
+    int check_every = 0;
+    int profile = 0;
+    double tol = 0;
+    i64 mxLoop = 0;
+    i64 sweeps_launched = 0;
+    int nblk_norm = 0;
+    int h_nactive = 0;
+    FusedPlan fused{};
+};
+
+struct xinv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // xinv_timer_*
+    std::vector<cudaEvent_t> prof_ev;   // pairs (begin, end) around the dominant kernels
+    size_t prof_used = 0;
+    // workspace (grown on demand, reused across calls)
+    DevBuf stage[10];            // staged S, S2 and up to 8 coefficient arrays
+    DevBuf state, psum, pcnt, ticket, nactive;
+    int *h_nactive_pinned = nullptr;
+    Problem pb;
+    xinv_stats stats{};
+    // NCCL (loaded lazily with dlopen)
+    void *nccl_lib = nullptr;
+    void *nccl_comm = nullptr;
+    DevBuf nccl_buf;
+    int nccl_rank = 0, nccl_world = 1;
+};
+
+static int ensure(DevBuf &b, size_t bytes)
+{
+    if (b.bytes >= bytes && b.p) return XINV_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess)
+        return set_err(XINV_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    b.bytes = bytes;
+    return XINV_OK;
+}
+
+static void release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+extern "C" const char *xinv_last_error(void) { return g_err; }
+extern "C" int xinv_version(void) { return XINV_VERSION; }
+
+extern "C" int xinv_device_count(int *out)
+{
+    if (!out) return set_err(XINV_E_ARG, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *out = 0; return set_err(XINV_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *out = n;
+    return XINV_OK;
+}
+
+static int create_common(xinv_ctx **out, int device, void *stream, bool own)
+{
+    if (!out) return set_err(XINV_E_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return set_err(XINV_E_ARG, "device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_err(XINV_E_UNSUPPORTED, "device %d is sm_%d%d; libxinv_b200 is built for sm_100a only",
+                       device, prop.major, prop.minor);
+    xinv_ctx *c = new xinv_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (own) {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    } else {
+        c->stream = (cudaStream_t)stream;
+    }
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    CK(cudaEventCreate(&c->tm0));
+    CK(cudaEventCreate(&c->tm1));
+    CK(cudaHostAlloc((void **)&c->h_nactive_pinned, 64, cudaHostAllocDefault));
+    *out = c;
+    return XINV_OK;
+}
+
+extern "C" int xinv_create(xinv_ctx **out, int device) { return create_common(out, device, nullptr, true); }
+extern "C" int xinv_create_on_stream(xinv_ctx **out, int device, void *s) { return create_common(out, device, s, false); }
+
+extern "C" int xinv_nccl_finalize(xinv_ctx *ctx);
+
+extern "C" void xinv_destroy(xinv_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    xinv_nccl_finalize(c);
+    for (auto &b : c->stage) release(b);
+    release(c->state); release(c->psum); release(c->pcnt); release(c->ticket); release(c->nactive);
+    release(c->nccl_buf);
+    fused_plan_release(c->pb.fused);
+    if (c->h_nactive_pinned) cudaFreeHost(c->h_nactive_pinned);
+    for (auto e : c->prof_ev) cudaEventDestroy(e);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->tm0) cudaEventDestroy(c->tm0);
+    if (c->tm1) cudaEventDestroy(c->tm1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int xinv_get_stats(const xinv_ctx *c, xinv_stats *out)
+{
+    if (!c || !out) return set_err(XINV_E_ARG, "NULL argument");
+    *out = c->stats;
+    return XINV_OK;
+}
+
+extern "C" int xinv_synchronize(xinv_ctx *c)
+{
+    if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return XINV_OK;
+}
+
+extern "C" int xinv_timer_start(xinv_ctx *c)
+{
+    if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->tm0, c->stream));
+    return XINV_OK;
+}
+
+extern "C" int xinv_timer_stop(xinv_ctx *c, double *ms_out)
+{
+    if (!c || !ms_out) return set_err(XINV_E_ARG, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->tm1, c->stream));
+    CK(cudaEventSynchronize(c->tm1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->tm0, c->tm1));
+    *ms_out = ms;
+    return XINV_OK;
+}
+
+extern "C" int xinv_host_alloc(void **out, int64_t bytes)
+{
+    if (!out || bytes < 0) return set_err(XINV_E_ARG, "bad argument");
+    CK(cudaHostAlloc(out, (size_t)(bytes ? bytes : 16), cudaHostAllocDefault));
+    return XINV_OK;
+}
+extern "C" int xinv_host_free(void *p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return XINV_OK;
+}
+extern "C" int xinv_dev_alloc(xinv_ctx *c, void **out, int64_t bytes)
+{
+    if (!c || !out || bytes < 0) return set_err(XINV_E_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMalloc(out, (size_t)(bytes ? bytes : 16)));
+    return XINV_OK;
+}
+extern "C" int xinv_dev_free(xinv_ctx *c, void *p)
+{
+    if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    if (p) CK(cudaFree(p));
+    return XINV_OK;
+}
+extern "C" int xinv_memcpy_h2d(xinv_ctx *c, void *dst, const void *src, int64_t bytes)
+{
+    if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return XINV_OK;
+}
+extern "C" int xinv_memcpy_d2h(xinv_ctx *c, void *dst, const void *src, int64_t bytes)
+{
+    if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return XINV_OK;
+}
+
+// ---------------------------------------------------------------------------
+// begin: validate, stage, initialise per-slice state
+// ---------------------------------------------------------------------------
+__global__ void xd_init_state_kernel(XdSliceState *st, const double *flags_in, int batch, int *nactive)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *nactive = batch;
+    if (b >= batch) return;
+    XdSliceState s;
+    s.normPrev = DBL_MAX;                  // numbas.py:280 np.finfo(np.float64).max
+    s.flags[0] = flags_in[3 * b + 0];
+    s.flags[1] = flags_in[3 * b + 1];
+    s.flags[2] = flags_in[3 * b + 2];
+    s.loop = 0;
+    s.active = 1;
+    s.sweeps_done = 0;
+    st[b] = s;
+}
+
+static int valid_bc(int bc) { return bc == XINV_BC_FIXED || bc == XINV_BC_EXTEND || bc == XINV_BC_PERIODIC; }
+
+struct BeginArgs {
+    int kind;
+    double *S;
+    const double *coef[8];
+    int ncoef;
+    int b_index;            // index of the optional B array in coef[] (or -1)
+    i64 batch, nz, ny, nx;
+    int bcy, bcx;
+    double p[6];
+    double optArg, undef;
+    double *flags;
+    i64 mxLoop;
+    double tol;
+    const xinv_opts *opts;
+};
+
+static int problem_begin(xinv_ctx *c, const BeginArgs &a)
+{
+    if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
+    if (c->pb.open) return set_err(XINV_E_STATE, "a problem is already open on this ctx (call xinv_end)");
+    if (!a.S || !a.flags) return set_err(XINV_E_ARG, "S and flags must not be NULL");
+    if (a.batch < 0 || a.nz < 1 || a.ny < 1 || a.nx < 1) return set_err(XINV_E_ARG, "bad sizes batch=%lld nz=%lld ny=%lld nx=%lld", a.batch, a.nz, a.ny, a.nx);
+    if (a.batch > 65535) return set_err(XINV_E_ARG, "batch %lld > 65535: split the call", a.batch);
+    if (a.nx > 0x3fffffff || a.ny > 0x3fffffff) return set_err(XINV_E_ARG, "grid too large");
+    if (!valid_bc(a.bcy) || !valid_bc(a.bcx)) return set_err(XINV_E_ARG, "bad boundary condition code");
+    if (a.bcy == XINV_BC_EXTEND && a.ny < 2) return set_err(XINV_E_ARG, "'extend' needs ny >= 2");
+    if (a.mxLoop < 0) return set_err(XINV_E_ARG, "mxLoop < 0");
+    for (int m = 0; m < a.ncoef; ++m)
+        if (!a.coef[m] && m != a.b_index) return set_err(XINV_E_ARG, "coefficient array %d is NULL", m);
+
+    xinv_opts o;
+    memset(&o, 0, sizeof o);
+    for (int m = 0; m < 8; ++m) o.coef_stride[m] = -1;
+    if (a.opts) {
+        if (a.opts->struct_size != (int32_t)sizeof(xinv_opts))
+            return set_err(XINV_E_ARG, "opts.struct_size %d != %zu", a.opts->struct_size, sizeof(xinv_opts));
+        o = *a.opts;
+    }
+    if (o.ordering != XINV_ORDER_COLOUR && o.ordering != XINV_ORDER_LEX) return set_err(XINV_E_ARG, "bad ordering");
+    if (o.mem_space != XINV_MEM_HOST && o.mem_space != XINV_MEM_DEVICE) return set_err(XINV_E_ARG, "bad mem_space");
+
+    CK(cudaSetDevice(c->device));
+    Problem &pb = c->pb;
+    fused_plan_release(pb.fused);
+    pb = Problem();
+    pb.kind = a.kind;
+    pb.batch = a.batch;
+    pb.hasB = (a.b_index >= 0 && a.coef[a.b_index] != nullptr);
+    pb.zero_exit = (a.kind == XD_STD2D);
+    pb.userS = a.S;
+    pb.userFlags = a.flags;
+    pb.mem_space = o.mem_space;
+    pb.ordering = o.ordering;
+    pb.check_every = o.check_every;
+    pb.profile = o.profile;
+    pb.tol = a.tol;
+    pb.mxLoop = a.mxLoop;
+    XdGeom &g = pb.g;
+    g.nz = a.nz; g.ny = a.ny; g.nx = a.nx;
+    g.N = a.nz * a.ny * a.nx;
+    g.bcy = a.bcy; g.bcx = a.bcx;
+    g.i0 = (a.bcx == XINV_BC_PERIODIC) ? 0 : 1;
+    g.i1 = (a.bcx == XINV_BC_PERIODIC) ? (int)a.nx : (int)a.nx - 1;
+    g.scheme = (pb.hasB && a.kind != XD_STD3D) ? 4 : 2;
+    g.wrapfix = (a.bcx == XINV_BC_PERIODIC) && (a.nx & 1);
+    g.ncol = xd_num_colours(g.scheme, g.wrapfix);
+    for (int m = 0; m < 6; ++m) pb.q.p[m] = a.p[m];
+    pb.q.optArg = a.optArg;
+    pb.q.undef = a.undef;
+
+    memset(&c->stats, 0, sizeof c->stats);
+    c->stats.ncolours = g.ncol;
+    if (a.batch == 0) { pb.open = true; pb.h_nactive = 0; return XINV_OK; }
+
+    if (pb.ordering == XINV_ORDER_LEX) {
+        if (pb.hasB && a.bcx == XINV_BC_PERIODIC)
+            return set_err(XINV_E_UNSUPPORTED, "lexicographic ordering with a 9-point stencil and periodic-x "
+                                               "serialises completely; not offered on the GPU");
+    }
+
+    // ---- staging --------------------------------------------------------
+    const size_t slice_bytes = (size_t)g.N * sizeof(double);
+    cudaEvent_t e0 = c->ev0, e1 = c->ev1;
+    if (pb.mem_space == XINV_MEM_HOST) {
+        CK(cudaEventRecord(e0, c->stream));
+        int rc = ensure(c->stage[0], slice_bytes * a.batch);
+        if (rc) return rc;
+        pb.dS = (double *)c->stage[0].p;
+        CK(cudaMemcpyAsync(pb.dS, a.S, slice_bytes * a.batch, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (i64)(slice_bytes * a.batch);
+        for (int m = 0; m < a.ncoef; ++m) {
+            if (!a.coef[m]) { pb.q.c[m] = nullptr; pb.q.cs[m] = 0; continue; }
+            const i64 stride = (o.coef_stride[m] < 0) ? g.N : o.coef_stride[m];
+            if (stride != 0 && stride != g.N) return set_err(XINV_E_ARG, "coef_stride[%d]=%lld must be -1, 0 or the slice size for host staging", m, stride);
+            const size_t bytes = (stride == 0) ? slice_bytes : slice_bytes * a.batch;
+            rc = ensure(c->stage[2 + m], bytes);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(c->stage[2 + m].p, a.coef[m], bytes, cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2d_bytes += (i64)bytes;
+            pb.q.c[m] = (const double *)c->stage[2 + m].p;
+            pb.q.cs[m] = stride;
+        }
+        CK(cudaEventRecord(e1, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        c->stats.h2d_ms = ms;
+    } else {
+        pb.dS = a.S;
+        for (int m = 0; m < a.ncoef; ++m) {
+            pb.q.c[m] = a.coef[m];
+            pb.q.cs[m] = (!a.coef[m]) ? 0 : ((o.coef_stride[m] < 0) ? g.N : o.coef_stride[m]);
+        }
+    }
+
+    // ---- per-slice state ----------------------------------------------------
+    int rc;
+    if ((rc = ensure(c->state, sizeof(XdSliceState) * a.batch))) return rc;
+    if ((rc = ensure(c->nactive, 64))) return rc;
+    if ((rc = ensure(c->ticket, sizeof(unsigned) * a.batch))) return rc;
+    // flags in -> device (reuse psum buffer temporarily is awkward; use a small staging alloc)
+    DevBuf ftmp;
+    if ((rc = ensure(ftmp, sizeof(double) * 3 * a.batch))) return rc;
+    CK(cudaMemcpyAsync(ftmp.p, a.flags, sizeof(double) * 3 * a.batch, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->ticket.p, 0, sizeof(unsigned) * a.batch, c->stream));
+    xd_init_state_kernel<<<(unsigned)((a.batch + 127) / 128), 128, 0, c->stream>>>(
+        (XdSliceState *)c->state.p, (const double *)ftmp.p, (int)a.batch, (int *)c->nactive.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    release(ftmp);
+    pb.h_nactive = (int)a.batch;
+
+    // norm partial layout: enough blocks to fill the machine, few enough that the
+    // last-block pass stays trivial
+    {
+        i64 want = (g.N + (i64)XD_NORM_THREADS * 8 - 1) / ((i64)XD_NORM_THREADS * 8);
+        i64 per_slice_max = (4LL * c->sm_count + a.batch - 1) / a.batch;
+        if (per_slice_max < 1) per_slice_max = 1;
+        if (want > per_slice_max) want = per_slice_max;
+        if (want < 1) want = 1;
+        if (want > 1024) want = 1024;
+        pb.nblk_norm = (int)want;
+    }
+
+    // ---- engine choice ----------------------------------------------------
+    pb.engine = XINV_ENGINE_COLOUR;
+    if (pb.ordering == XINV_ORDER_COLOUR && o.engine != XINV_ENGINE_COLOUR) {
+        std::string why;
+        if (fused_plan_supported(pb.kind, pb.hasB, g, why)) {
+            // the fused engine ping-pongs between two S buffers
+            if ((rc = ensure(c->stage[1], slice_bytes * a.batch))) return rc;
+            pb.dS2 = (double *)c->stage[1].p;
+            rc = fused_plan_build(pb.fused, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, pb.dS2, c->stream, why);
+            if (rc == 0) pb.engine = XINV_ENGINE_FUSED;
+            else if (o.engine == XINV_ENGINE_FUSED)
+                return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
+        } else if (o.engine == XINV_ENGINE_FUSED) {
+            return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
+        }
+    }
+    {
+        int np = pb.nblk_norm;
+        if (pb.engine == XINV_ENGINE_FUSED && pb.fused.nblk_partials > np) np = pb.fused.nblk_partials;
+        if ((rc = ensure(c->psum, sizeof(double) * a.batch * np))) return rc;
+        if ((rc = ensure(c->pcnt, sizeof(i64) * a.batch * np))) return rc;
+    }
+    c->stats.engine = pb.engine;
+    pb.open = true;
+    return XINV_OK;
+}
+
+// ---------------------------------------------------------------------------
+// one sweep (all colours + norm/decide) on every active slice
+// ---------------------------------------------------------------------------
+template <int KIND>
+static void launch_colour(xinv_ctx *c, Problem &pb, int colour, dim3 grid, int nxblk)
+{
+    XdSliceState *st = (XdSliceState *)c->state.p;
+    if (pb.hasB && KIND != XD_STD3D)
+        xd_sweep_colour_kernel<KIND, true><<<grid, XD_SWEEP_THREADS, 0, c->stream>>>(pb.dS, pb.q, pb.g, colour, nxblk, st);
+    else
+        xd_sweep_colour_kernel<KIND, false><<<grid, XD_SWEEP_THREADS, 0, c->stream>>>(pb.dS, pb.q, pb.g, colour, nxblk, st);
+}
+
+static void prof_mark(xinv_ctx *c, const Problem &pb)
+{
+    if (!pb.profile) return;
+    if (c->prof_used == c->prof_ev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c->prof_ev.push_back(e);
+    }
+    cudaEventRecord(c->prof_ev[c->prof_used++], c->stream);
+}
+
+static void prof_collect(xinv_ctx *c, int launches_per_pair)
+{
+    for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]) == cudaSuccess) {
+            c->stats.dom_ms += ms;
+            c->stats.dom_launches += launches_per_pair;
+        }
+    }
+    c->prof_used = 0;
+}
+
+static int sweep_colour_engine(xinv_ctx *c, Problem &pb)
+{
+    const XdGeom &g = pb.g;
+    XdSliceState *st = (XdSliceState *)c->state.p;
+    if (g.bcy == XINV_BC_EXTEND) {
+        const i64 levels = (g.nz > 1) ? g.nz - 2 : 1;
+        if (levels > 0) {
+            dim3 grid((unsigned)((g.nx + 127) / 128), (unsigned)levels, (unsigned)pb.batch);
+            xd_extend_kernel<<<grid, 128, 0, c->stream>>>(pb.dS, g, pb.q.undef, st);
+            c->stats.kernel_launches++;
+        }
+    }
+    const i64 rows = (g.ny >= 3 ? g.ny - 2 : 0) * (pb.kind == XD_STD3D ? (g.nz >= 3 ? g.nz - 2 : 0) : 1);
+    const int base = (g.scheme == 4) ? 4 : 2;
+    if (rows > 0 && g.i1 > g.i0) {
+        prof_mark(c, pb);
+        for (int col = 0; col < g.ncol; ++col) {
+            int nxblk;
+            if (col >= base) nxblk = 1;
+            else nxblk = (int)(((g.nx + 1) / 2 + XD_SWEEP_THREADS - 1) / XD_SWEEP_THREADS);
+            dim3 grid((unsigned)(rows * nxblk), (unsigned)pb.batch, 1);
+            if (pb.kind == XD_STD2D) launch_colour<XD_STD2D>(c, pb, col, grid, nxblk);
+            else if (pb.kind == XD_GEN2D) launch_colour<XD_GEN2D>(c, pb, col, grid, nxblk);
+            else launch_colour<XD_STD3D>(c, pb, col, grid, nxblk);
+            c->stats.kernel_launches++;
+        }
+        prof_mark(c, pb);
+    }
+    dim3 ngrid((unsigned)pb.nblk_norm, (unsigned)pb.batch, 1);
+    xd_norm_decide_kernel<<<ngrid, XD_NORM_THREADS, 0, c->stream>>>(
+        pb.dS, g.N, pb.q.undef, pb.nblk_norm, (double *)c->psum.p, (i64 *)c->pcnt.p,
+        (unsigned *)c->ticket.p, st, (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit);
+    c->stats.kernel_launches++;
+    return XINV_OK;
+}
+
+static int auto_check_every(const xinv_ctx *c, const Problem &pb)
+{
+    if (pb.check_every > 0) return pb.check_every;
+    // aim at ~300 us of device work between host polls; a sweep moves ~80 B/cell
+    const double est_us = 4.0 + (double)pb.g.N * (double)pb.batch * 80.0 / 4.0e6;  // 4 TB/s = 4e6 B/us
+    int k = (int)(300.0 / est_us);
+    if (k < 4) k = 4;
+    if (k > 64) k = 64;
+    (void)c;
+    return k;
+}
+
+extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
+{
+    if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
+    Problem &pb = c->pb;
+    if (!pb.open) return set_err(XINV_E_STATE, "no open problem (call xinv_*_begin first)");
+    CK(cudaSetDevice(c->device));
+    if (pb.batch == 0 || pb.h_nactive == 0) { if (n_active_out) *n_active_out = 0; return XINV_OK; }
+    const i64 remaining = (pb.mxLoop + 1) - pb.sweeps_launched;   // at most mxLoop+1 sweeps (numbas.py:410)
+    if (sweeps <= 0) sweeps = auto_check_every(c, pb);
+    if (sweeps > remaining) sweeps = remaining;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (i64 it = 0; it < sweeps; ++it) {
+        int rc;
+        if (pb.ordering == XINV_ORDER_LEX)
+            rc = lex_sweep(c->stream, pb.kind, pb.hasB, pb.g, pb.q, pb.batch, pb.dS, (XdSliceState *)c->state.p,
+                           pb.nblk_norm, (double *)c->psum.p, (i64 *)c->pcnt.p, (unsigned *)c->ticket.p,
+                           (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
+        else if (pb.engine == XINV_ENGINE_FUSED)
+            rc = fused_sweep(pb.fused, c->stream, (XdSliceState *)c->state.p, (double *)c->psum.p, (i64 *)c->pcnt.p,
+                             (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
+        else
+            rc = sweep_colour_engine(c, pb);
+        if (rc) return rc;
+    }
+    pb.sweeps_launched += sweeps;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_nactive_pinned, c->nactive.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.solve_ms += ms;
+    if (pb.profile) prof_collect(c, pb.engine == XINV_ENGINE_FUSED ? 1 : pb.g.ncol);
+    c->stats.sweeps_launched = pb.sweeps_launched;
+    pb.h_nactive = *c->h_nactive_pinned;
+    if (pb.h_nactive != 0 && pb.sweeps_launched >= pb.mxLoop + 1)
+        return set_err(XINV_E_STATE, "internal error: %d slices still active after mxLoop+1 sweeps", pb.h_nactive);
+    if (n_active_out) *n_active_out = pb.h_nactive;
+    return XINV_OK;
+}
+
+// gather per-slice results of the ping-pong engine into dS
+__global__ void xd_gather_pingpong_kernel(double *__restrict__ dst, const double *__restrict__ other,
+                                          i64 N, const XdSliceState *__restrict__ st)
+{
+    const int b = blockIdx.y;
+    if ((st[b].sweeps_done & 1) == 0) return;       // even number of sweeps: result already in dst
+    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) dst[(i64)b * N + p] = other[(i64)b * N + p];
+}
+
+extern "C" int xinv_end(xinv_ctx *c)
+{
+    if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
+    Problem &pb = c->pb;
+    if (!pb.open) return set_err(XINV_E_STATE, "no open problem");
+    CK(cudaSetDevice(c->device));
+    pb.open = false;
+    if (pb.batch == 0) return XINV_OK;
+    const XdGeom &g = pb.g;
+    if (pb.engine == XINV_ENGINE_FUSED) {
+        dim3 grid((unsigned)((g.N + 255) / 256), (unsigned)pb.batch);
+        xd_gather_pingpong_kernel<<<grid, 256, 0, c->stream>>>(pb.dS, pb.dS2, g.N, (const XdSliceState *)c->state.p);
+        c->stats.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    std::vector<XdSliceState> hs((size_t)pb.batch);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (pb.mem_space == XINV_MEM_HOST) {
+        CK(cudaMemcpyAsync(pb.userS, pb.dS, sizeof(double) * g.N * pb.batch, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += (i64)sizeof(double) * g.N * pb.batch;
+    }
+    CK(cudaMemcpyAsync(hs.data(), c->state.p, sizeof(XdSliceState) * pb.batch, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.d2h_ms = ms;
+    i64 updates = 0;
+    for (i64 b = 0; b < pb.batch; ++b) {
+        pb.userFlags[3 * b + 0] = hs[b].flags[0];
+        pb.userFlags[3 * b + 1] = hs[b].flags[1];
+        pb.userFlags[3 * b + 2] = hs[b].flags[2];
+        updates += (i64)hs[b].sweeps_done * g.N;
+    }
+    c->stats.cell_updates = updates;
+    c->stats.sweep_ms = pb.sweeps_launched ? c->stats.solve_ms / (double)pb.sweeps_launched : 0.0;
+    return XINV_OK;
+}
+
+static int run_to_completion(xinv_ctx *c)
+{
+    int64_t na = 1;
+    int rc = XINV_OK;
+    while (na > 0) {
+        rc = xinv_step(c, 0, &na);
+        if (rc) break;
+    }
+    int rc2 = xinv_end(c);
+    return rc ? rc : rc2;
+}
+
+// ---------------------------------------------------------------------------
+// extern "C" solvers
+// ---------------------------------------------------------------------------
+extern "C" int xinv_std2d_begin(xinv_ctx *ctx, double *S, const double *A, const double *B,
+                                const double *C, const double *F,
+                                int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                                double delxSqr, double ratioQtr, double ratioSqr,
+                                double optArg, double undef, double *flags,
+                                int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    BeginArgs a{};
+    a.kind = XD_STD2D; a.S = S;
+    a.coef[0] = A; a.coef[1] = B; a.coef[2] = C; a.coef[3] = F; a.ncoef = 4; a.b_index = 1;
+    a.batch = batch; a.nz = 1; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delxSqr; a.p[1] = ratioQtr; a.p[2] = ratioSqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    return problem_begin(ctx, a);
+}
+
+extern "C" int xinv_gen2d_begin(xinv_ctx *ctx, double *S, const double *A, const double *B,
+                                const double *C, const double *D, const double *E,
+                                const double *F, const double *G,
+                                int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                                double delx, double delxSqr, double ratio, double ratioQtr,
+                                double ratioSqr, double optArg, double undef, double *flags,
+                                int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    BeginArgs a{};
+    a.kind = XD_GEN2D; a.S = S;
+    a.coef[0] = A; a.coef[1] = B; a.coef[2] = C; a.coef[3] = D; a.coef[4] = E; a.coef[5] = F; a.coef[6] = G;
+    a.ncoef = 7; a.b_index = 1;
+    a.batch = batch; a.nz = 1; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delx; a.p[1] = delxSqr; a.p[2] = ratio; a.p[3] = ratioQtr; a.p[4] = ratioSqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    return problem_begin(ctx, a);
+}
+
+extern "C" int xinv_std3d_begin(xinv_ctx *ctx, double *S, const double *A, const double *B,
+                                const double *C, const double *F,
+                                int64_t batch, int64_t nz, int64_t ny, int64_t nx,
+                                int bcz, int bcy, int bcx,
+                                double delxSqr, double ratio2Sqr, double ratio1Sqr,
+                                double optArg, double undef, double *flags,
+                                int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    if (!valid_bc(bcz)) return set_err(XINV_E_ARG, "bad boundary condition code");
+    BeginArgs a{};
+    a.kind = XD_STD3D; a.S = S;
+    a.coef[0] = A; a.coef[1] = B; a.coef[2] = C; a.coef[3] = F; a.ncoef = 4; a.b_index = -1;
+    a.batch = batch; a.nz = nz; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delxSqr; a.p[1] = ratio2Sqr; a.p[2] = ratio1Sqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    return problem_begin(ctx, a);
+}
+
+extern "C" int xinv_std2d(xinv_ctx *ctx, double *S, const double *A, const double *B,
+                          const double *C, const double *F,
+                          int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                          double delxSqr, double ratioQtr, double ratioSqr,
+                          double optArg, double undef, double *flags,
+                          int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    int rc = xinv_std2d_begin(ctx, S, A, B, C, F, batch, ny, nx, bcy, bcx, delxSqr, ratioQtr, ratioSqr,
+                              optArg, undef, flags, mxLoop, tolerance, opts);
+    if (rc) return rc;
+    return run_to_completion(ctx);
+}
+
+extern "C" int xinv_gen2d(xinv_ctx *ctx, double *S, const double *A, const double *B,
+                          const double *C, const double *D, const double *E,
+                          const double *F, const double *G,
+                          int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                          double delx, double delxSqr, double ratio, double ratioQtr,
+                          double ratioSqr, double optArg, double undef, double *flags,
+                          int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    int rc = xinv_gen2d_begin(ctx, S, A, B, C, D, E, F, G, batch, ny, nx, bcy, bcx, delx, delxSqr, ratio,
+                              ratioQtr, ratioSqr, optArg, undef, flags, mxLoop, tolerance, opts);
+    if (rc) return rc;
+    return run_to_completion(ctx);
+}
+
+extern "C" int xinv_std3d(xinv_ctx *ctx, double *S, const double *A, const double *B,
+                          const double *C, const double *F,
+                          int64_t batch, int64_t nz, int64_t ny, int64_t nx,
+                          int bcz, int bcy, int bcx,
+                          double delxSqr, double ratio2Sqr, double ratio1Sqr,
+                          double optArg, double undef, double *flags,
+                          int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    int rc = xinv_std3d_begin(ctx, S, A, B, C, F, batch, nz, ny, nx, bcz, bcy, bcx, delxSqr, ratio2Sqr,
+                              ratio1Sqr, optArg, undef, flags, mxLoop, tolerance, opts);
+    if (rc) return rc;
+    return run_to_completion(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// NCCL (dlopen'ed so the library loads on machines without it)
+// ---------------------------------------------------------------------------
+typedef struct { char internal[128]; } xnccl_uid;
+typedef int (*nccl_get_uid_t)(xnccl_uid *);
+typedef int (*nccl_init_rank_t)(void **, int, xnccl_uid, int);
+typedef int (*nccl_allreduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_destroy_t)(void *);
+typedef const char *(*nccl_errstr_t)(int);
+
+static void *g_nccl = nullptr;
+static void *nccl_handle()
+{
+    if (g_nccl) return g_nccl;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    const char *env = getenv("XINV_NCCL_LIB");
+    if (env) g_nccl = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    for (int i = 0; !g_nccl && names[i]; ++i) g_nccl = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    return g_nccl;
+}
+
+extern "C" int xinv_nccl_unique_id(void *id128)
+{
+    if (!id128) return set_err(XINV_E_ARG, "id buffer is NULL");
+    void *h = nccl_handle();
+    if (!h) return set_err(XINV_E_NCCL, "libnccl.so.2 not found (set XINV_NCCL_LIB): %s", dlerror());
+    nccl_get_uid_t f = (nccl_get_uid_t)dlsym(h, "ncclGetUniqueId");
+    if (!f) return set_err(XINV_E_NCCL, "ncclGetUniqueId missing");
+    xnccl_uid id;
+    int r = f(&id);
+    if (r) return set_err(XINV_E_NCCL, "ncclGetUniqueId -> %d", r);
+    memcpy(id128, &id, 128);
+    return XINV_OK;
+}
+
+extern "C" int xinv_nccl_init(xinv_ctx *c, const void *id128, int rank, int world)
+{
+    if (!c || !id128) return set_err(XINV_E_ARG, "NULL argument");
+    void *h = nccl_handle();
+    if (!h) return set_err(XINV_E_NCCL, "libnccl.so.2 not found (set XINV_NCCL_LIB)");
+    nccl_init_rank_t f = (nccl_init_rank_t)dlsym(h, "ncclCommInitRank");
+    if (!f) return set_err(XINV_E_NCCL, "ncclCommInitRank missing");
+    CK(cudaSetDevice(c->device));
+    xnccl_uid id;
+    memcpy(&id, id128, 128);
+    void *comm = nullptr;
+    int r = f(&comm, world, id, rank);
+    if (r) return set_err(XINV_E_NCCL, "ncclCommInitRank -> %d", r);
+    c->nccl_comm = comm;
+    c->nccl_rank = rank;
+    c->nccl_world = world;
+    int rc = ensure(c->nccl_buf, 64);
+    return rc;
+}
+
+extern "C" int xinv_nccl_allreduce_active(xinv_ctx *c, int64_t local, int64_t *global_out)
+{
+    if (!c || !global_out) return set_err(XINV_E_ARG, "NULL argument");
+    if (!c->nccl_comm) return set_err(XINV_E_STATE, "xinv_nccl_init not called");
+    nccl_allreduce_t f = (nccl_allreduce_t)dlsym(nccl_handle(), "ncclAllReduce");
+    if (!f) return set_err(XINV_E_NCCL, "ncclAllReduce missing");
+    CK(cudaSetDevice(c->device));
+    i64 *d = (i64 *)c->nccl_buf.p;
+    CK(cudaMemcpyAsync(d, &local, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    const int ncclInt64 = 4, ncclSum = 0;
+    int r = f(d, d + 1, 1, ncclInt64, ncclSum, c->nccl_comm, c->stream);
+    if (r) return set_err(XINV_E_NCCL, "ncclAllReduce -> %d", r);
+    i64 out = 0;
+    CK(cudaMemcpyAsync(&out, d + 1, sizeof(i64), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *global_out = out;
+    return XINV_OK;
+}
+
+extern "C" int xinv_nccl_finalize(xinv_ctx *c)
+{
+    if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
+    if (c->nccl_comm) {
+        nccl_destroy_t f = (nccl_destroy_t)dlsym(nccl_handle(), "ncclCommDestroy");
+        if (f) f(c->nccl_comm);
+        c->nccl_comm = nullptr;
+    }
+    return XINV_OK;
+}

@@ -1,0 +1,218 @@
+// xinv_device.cuh -- device-side building blocks shared by every engine:
+// colourings, the per-cell SOR updates (one IEEE binary64 operation per
+// +,-,*,/ of the reference expression, in the reference's evaluation order;
+// the translation unit is compiled with -fmad=false so nothing is contracted),
+// and deterministic block reductions.
+//
+// Reference semantics followed here (file:line in /root/reference/xinvert):
+//   invert_standard_2D  numbas.py:344-369 (+ west/east columns :315-340, :374-399)
+//   invert_general_2D   numbas.py:1126-1153 (+ :1095-1122, :1157-1184)
+//   invert_standard_3D  numbas.py:147-169 (+ :121-143, :173-195)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef long long i64;
+
+#define XD_BC_FIXED    0
+#define XD_BC_EXTEND   1
+#define XD_BC_PERIODIC 2
+
+// ---------------------------------------------------------------------------
+// Colourings.  2-colour scheme: parity of the index sum (5-/7-point stencils).
+// 4-colour scheme: 2*(j&1)+(i&1) (9-point stencil).  With periodic-x and odd nx
+// the wrap neighbours (columns 0 and nx-1) would share a colour, so column nx-1
+// is moved to two extra colours indexed by row parity ("wrap-fix").
+// (The test oracle restates this colouring independently; tests compare them.)
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int xd_num_colours(int scheme, int wrapfix)
+{
+    return (scheme == 4 ? 4 : 2) + (wrapfix ? 2 : 0);
+}
+
+__host__ __device__ __forceinline__ int xd_colour(int scheme, int wrapfix, i64 nx, i64 jk, i64 j, i64 i)
+{
+    // jk = j (2-D) or j+k (3-D): the row-parity that enters the 2-colour scheme
+    if (scheme == 4) {
+        if (wrapfix && i == nx - 1) return 4 + (int)(j & 1);
+        return 2 * (int)(j & 1) + (int)(i & 1);
+    }
+    if (wrapfix && i == nx - 1) return 2 + (int)(jk & 1);
+    return (int)((i + jk) & 1);
+}
+
+// ---------------------------------------------------------------------------
+// Kernel argument blocks (passed by value)
+// ---------------------------------------------------------------------------
+struct XdGeom {
+    i64 nz, ny, nx;       // nz == 1 for 2-D problems
+    i64 N;                // cells per slice
+    int bcy, bcx;
+    int i0, i1;           // updated columns [i0, i1)
+    int scheme, wrapfix, ncol;
+};
+
+struct XdCoef {
+    const double *c[8];   // coefficient / forcing arrays in C-ABI argument order
+    i64 cs[8];            // batch stride of each (elements); 0 = shared by batch
+    double p[6];          // scalar parameters, meaning per problem kind
+    double optArg, undef;
+};
+
+// ---------------------------------------------------------------------------
+// Per-cell updates.  S points at the slice; idx helpers take (row offset, col).
+// ---------------------------------------------------------------------------
+
+// standard 2-D.  c[] = {A,B,C,F}; p[] = {delxSqr, ratioQtr, ratioSqr}
+template <bool HASB>
+__device__ __forceinline__ void xd_update_std2d(double *__restrict__ S,
+    const double *__restrict__ A, const double *__restrict__ B,
+    const double *__restrict__ C, const double *__restrict__ F,
+    i64 nx, i64 j, i64 i, i64 ip, i64 im,
+    double delxSqr, double ratioQtr, double ratioSqr, double optArg, double undef)
+{
+    const i64 c = j * nx + i, n = c + nx, s = c - nx;
+    const i64 e = j * nx + ip, w = j * nx + im;
+    const double Fc = F[c], An = A[n], Ac = A[c], Ce = C[e], Cc = C[c];
+    bool cond = (Fc != undef) & (An != undef) & (Ac != undef) & (Ce != undef) & (Cc != undef);
+    double Be = 0, Bw = 0, Bn = 0, Bs = 0, Bq = 0;
+    if (HASB) {
+        Be = B[e]; Bw = B[w]; Bn = B[n]; Bs = B[s];
+        cond = cond & (Be != undef) & (Bw != undef) & (Bn != undef) & (Bs != undef);
+        Bq = (i == 0) ? B[n + 1] : Bn;            // numbas.py:327 west-column quirk
+    }
+    if (!cond) return;
+    const double Sc = S[c], Sn = S[n], Ss = S[s], Se = S[e], Sw = S[w];
+    const double t1 = (An * (Sn - Sc) - Ac * (Sc - Ss)) * ratioSqr;
+    const double t4 = (Ce * (Se - Sc) - Cc * (Sc - Sw));
+    double temp;
+    if (HASB) {
+        const double Sne = S[n - i + ip], Snw = S[n - i + im];
+        const double Sse = S[s - i + ip], Ssw = S[s - i + im];
+        const double Sse2 = (i == 0) ? Ss : Sse;  // numbas.py:328 west-column quirk
+        const double t2 = (Bq * (Sne - Snw) - Bs * (Sse2 - Ssw)) * ratioQtr;
+        const double t3 = (Be * (Sne - Sse) - Bw * (Snw - Ssw)) * ratioQtr;
+        temp = (((t1 + t2) + t3) + t4) - Fc * delxSqr;
+    } else {
+        temp = (t1 + t4) - Fc * delxSqr;
+    }
+    temp = temp * (optArg / ((An + Ac) * ratioSqr + (Ce + Cc)));
+    S[c] = Sc + temp;
+}
+
+// general 2-D.  c[] = {A,B,C,D,E,F,G}; p[] = {delx, delxSqr, ratio, ratioQtr, ratioSqr}
+template <bool HASB>
+__device__ __forceinline__ void xd_update_gen2d(double *__restrict__ S,
+    const double *__restrict__ A, const double *__restrict__ B,
+    const double *__restrict__ C, const double *__restrict__ D,
+    const double *__restrict__ E, const double *__restrict__ F,
+    const double *__restrict__ G,
+    i64 nx, i64 j, i64 i, i64 ip, i64 im,
+    double delx, double delxSqr, double ratio, double ratioQtr, double ratioSqr,
+    double optArg, double undef)
+{
+    const i64 c = j * nx + i, n = c + nx, s = c - nx;
+    const i64 e = j * nx + ip, w = j * nx + im;
+    const double Gc = G[c], Ac = A[c], Cc = C[c], Dc = D[c], Ec = E[c], Fc = F[c];
+    bool cond = (Gc != undef) & (Ac != undef) & (Cc != undef) & (Dc != undef) &
+                (Ec != undef) & (Fc != undef);
+    double Bc = 0;
+    if (HASB) { Bc = B[c]; cond = cond & (Bc != undef); }
+    if (!cond) return;
+    const double Sc = S[c], Sn = S[n], Ss = S[s], Se = S[e], Sw = S[w];
+    double temp = Ac * ((Sn - Sc) - (Sc - Ss)) * ratioSqr;
+    if (HASB) {
+        const double Sne = S[n - i + ip], Snw = S[n - i + im];
+        const double Sse = S[s - i + ip], Ssw = S[s - i + im];
+        temp = temp + Bc * ((Sne - Sse) - (Snw - Ssw)) * ratioQtr;
+    }
+    temp = temp + Cc * ((Se - Sc) - (Sc - Sw));
+    temp = temp + (Dc * (Sn - Ss) * ratio + Ec * (Se - Sw)) * delx / 2.0;
+    temp = temp + (Fc * Sc - Gc) * delxSqr;
+    temp = temp * (optArg / ((Ac * ratioSqr + Cc) * 2.0 - Fc * delxSqr));
+    S[c] = Sc + temp;
+}
+
+// standard 3-D.  c[] = {A,B,C,F}; p[] = {delxSqr, ratio2Sqr, ratio1Sqr}
+__device__ __forceinline__ void xd_update_std3d(double *__restrict__ S,
+    const double *__restrict__ A, const double *__restrict__ B,
+    const double *__restrict__ C, const double *__restrict__ F,
+    i64 ny, i64 nx, i64 k, i64 j, i64 i, i64 ip, i64 im,
+    double delxSqr, double ratio2Sqr, double ratio1Sqr, double optArg, double undef)
+{
+    const i64 pl = ny * nx;
+    const i64 row = k * pl + j * nx;
+    const i64 c = row + i, e = row + ip, w = row + im;
+    const i64 n = c + nx, s = c - nx, u = c + pl, d = c - pl;
+    const double Fc = F[c], Au = A[u], Ac = A[c], Bn = B[n], Bc = B[c], Ce = C[e], Cc = C[c];
+    const bool cond = (Fc != undef) & (Au != undef) & (Ac != undef) & (Bn != undef) &
+                      (Bc != undef) & (Ce != undef) & (Cc != undef);
+    if (!cond) return;
+    const double Sc = S[c];
+    double temp = (
+        (Au * (S[u] - Sc) - Ac * (Sc - S[d])) * ratio2Sqr +
+        (Bn * (S[n] - Sc) - Bc * (Sc - S[s])) * ratio1Sqr +
+        (Ce * (S[e] - Sc) - Cc * (Sc - S[w]))
+    ) - Fc * delxSqr;
+    temp = temp * (optArg / ((Au + Ac) * ratio2Sqr + (Bn + Bc) * ratio1Sqr + (Ce + Cc)));
+    S[c] = Sc + temp;
+}
+
+// ---------------------------------------------------------------------------
+// Deterministic block reduction of (sum, count): fixed shuffle tree inside a
+// warp, fixed order across warps.  Result valid in thread 0.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void xd_block_reduce(double &sum, i64 &cnt, double *sm_sum, i64 *sm_cnt)
+{
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { sm_sum[wid] = sum; sm_cnt[wid] = cnt; }
+    __syncthreads();
+    if (wid == 0) {
+        sum = (lane < nw) ? sm_sum[lane] : 0.0;
+        cnt = (lane < nw) ? sm_cnt[lane] : 0;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_down_sync(0xffffffffu, sum, o);
+            cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        }
+    }
+}
+
+// Per-slice loop state kept on the device between sweeps.
+struct XdSliceState {
+    double normPrev;
+    double flags[3];      // overflow, last relative change, last loop index
+    i64    loop;
+    int    active;
+    int    sweeps_done;   // sweeps actually executed on this slice
+};
+
+// Loop control of the reference after each sweep: numbas.py:401-414 (2-D
+// standard, with the norm==0 exit), :197-210 and :1186-1199 (no such exit).
+__device__ __forceinline__ void xd_decide(XdSliceState &st, double sum, i64 cnt,
+                                          double tol, i64 mxLoop, int zero_exit)
+{
+    double norm;
+    if (cnt != 0) norm = sum / (double)cnt;
+    else          norm = nan("");
+    st.sweeps_done += 1;
+    if (isnan(norm) || norm > 1e100) {
+        st.flags[0] = 1.0;
+        st.active = 0;
+        return;
+    }
+    st.flags[1] = fabs(norm - st.normPrev) / st.normPrev;
+    st.flags[2] = (double)st.loop;
+    if (st.flags[1] < tol || st.loop >= mxLoop || (zero_exit && norm == 0.0)) {
+        st.active = 0;
+        return;
+    }
+    st.normPrev = norm;
+    st.loop += 1;
+}

@@ -1,0 +1,217 @@
+"""ndarray-level face of the CUDA SOR path.
+
+Two layers:
+
+* ``solve_standard_2D / solve_general_2D / solve_standard_3D`` -- batched: every
+  leading (non-core) axis of ``S`` is flattened into the ``batch`` argument of
+  ONE C-ABI call (``include/xinv.h``).  This is what replaces the reference's
+  serial slice loop (``core.py:129-139``, ``:418-428``, ``:59-69``).
+* ``invert_standard_2D / invert_general_2D / invert_standard_3D`` -- single
+  slice, with the exact positional signatures of the reference's numba kernels
+  (``numbas.py:216-219``, ``:988-991``, ``:16-19``) so parity tests read like
+  calls into the reference.
+
+Arrays may be numpy arrays (host; staged by the library) or CUDA tensors /
+objects exposing ``data_ptr()`` (device; used in place).  There is no CPU
+implementation behind these functions.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_UNDEF = -9.99e8
+
+
+def _is_device_array(a):
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+def _host_f64(a, name):
+    """C-contiguous float64 view/copy of a host array (float32 inputs are
+    promoted; the reference would iterate in mixed precision for those)."""
+    arr = np.asarray(a)
+    if arr.dtype != np.float64 or not arr.flags["C_CONTIGUOUS"]:
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+    return arr
+
+
+class _Operands:
+    """Pointer + batch stride of S and of every coefficient array."""
+
+    def __init__(self, S, coefs, core_ndim):
+        self.device = _is_device_array(S)
+        self.keep = []                      # keep temporaries alive during the call
+        if self.device:
+            import torch
+            if S.dtype != torch.float64 or not S.is_contiguous():
+                raise ValueError("device S must be a contiguous float64 tensor")
+            self.shape = tuple(S.shape)
+            self.S_ptr = S.data_ptr()
+            self.S_host = None
+        else:
+            if not isinstance(S, np.ndarray):
+                raise TypeError("S must be a numpy array or a CUDA tensor (it is updated in place)")
+            self.shape = S.shape
+            Sc = _host_f64(S, "S")
+            self.S_host = Sc
+            self.S_orig = S
+            self.S_ptr = Sc.ctypes.data
+        if len(self.shape) < core_ndim:
+            raise ValueError(f"S needs at least {core_ndim} dimensions")
+        self.core = tuple(int(n) for n in self.shape[-core_ndim:])
+        self.batch = int(np.prod(self.shape[:-core_ndim], dtype=np.int64)) if len(self.shape) > core_ndim else 1
+        self.N = int(np.prod(self.core, dtype=np.int64))
+        self.ptrs, self.strides = [], []
+        for name, a in coefs:
+            if a is None:
+                self.ptrs.append(None)
+                self.strides.append(0)
+                continue
+            if _is_device_array(a) != self.device:
+                raise ValueError(f"{name}: S and coefficients must live in the same memory space")
+            if self.device:
+                import torch
+                if a.dtype != torch.float64 or not a.is_contiguous():
+                    raise ValueError(f"{name} must be a contiguous float64 tensor")
+                shp, ptr = tuple(a.shape), a.data_ptr()
+            else:
+                a = _host_f64(a, name)
+                self.keep.append(a)
+                shp, ptr = a.shape, a.ctypes.data
+            shp = tuple(int(n) for n in shp)
+            if shp == tuple(self.shape):
+                stride = self.N
+            elif shp[-core_ndim:] == self.core and all(d == 1 for d in shp[:-core_ndim]):
+                stride = 0                  # one slice shared by the whole batch
+            else:
+                raise ValueError(f"{name} has shape {shp}; expected {self.shape} or {self.core}")
+            self.ptrs.append(ptr)
+            self.strides.append(stride)
+
+    def finish(self):
+        """Copy the result back if S had to be converted for the call."""
+        if not self.device and self.S_host is not self.S_orig:
+            self.S_orig[...] = self.S_host
+
+
+def _flags_array(flags, batch):
+    """Host flags [batch][3], seeded from the caller's flags (numbas keeps the
+    incoming values when a slice overflows in its first sweep)."""
+    f = np.asarray(flags, dtype=np.float64)
+    if f.shape == (3,):
+        out = np.tile(f, (batch, 1))
+    elif f.shape == (batch, 3):
+        out = np.ascontiguousarray(f)
+    else:
+        raise ValueError(f"flags must have shape (3,) or ({batch}, 3)")
+    return np.ascontiguousarray(out, dtype=np.float64)
+
+
+def _zero_to_none(B):
+    """``B`` identically zero selects the 5-point red-black path (value-identical:
+    the cross terms are exactly 0)."""
+    if B is None:
+        return None
+    if _is_device_array(B):
+        return None if not bool((B != 0).any().item()) else B
+    Bn = np.asarray(B)
+    return None if not Bn.any() else B
+
+
+def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, profile=False):
+    L = _lib.load()
+    ctx = ctx or _lib.default_context()
+    opts = _lib.make_opts(ordering=ordering, mem_space=_lib.MEM_DEVICE if ops.device else _lib.MEM_HOST,
+                          engine=engine, check_every=check_every, coef_strides=ops.strides,
+                          profile=profile)
+    fl = _flags_array(flags, ops.batch)
+    ptr_args = [C.c_void_p(ops.S_ptr)] + [C.c_void_p(p) if p is not None else None for p in ops.ptrs]
+    fn = {"std2d": L.xinv_std2d, "gen2d": L.xinv_gen2d, "std3d": L.xinv_std3d}[kind]
+    rc = fn(ctx.handle, *ptr_args, *fn_args_tail(fl), C.byref(opts))
+    _lib.check(rc)
+    ops.finish()
+    return fl, ctx.stats()
+
+
+def solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg,
+                      undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
+                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False):
+    """Batched ``invert_standard_2D`` (numbas.py:215-416) over S[..., ny, nx], in place.
+
+    Returns ``(flags[batch, 3], stats)``."""
+    B = _zero_to_none(B)
+    ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("F", F)], 2)
+    ny, nx = ops.core
+    tail = lambda fl: (ops.batch, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
+                       float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
+                       C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("std2d", ops, tail, flags, ordering, engine, check_every, ctx, profile)
+
+
+def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ratioQtr,
+                     ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
+                     tolerance=1e-8, ordering="colour", engine="auto", check_every=0, ctx=None, profile=False):
+    """Batched ``invert_general_2D`` (numbas.py:987-1201) over S[..., ny, nx], in place."""
+    B = _zero_to_none(B)
+    ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("D", D), ("E", E), ("F", F), ("G", G)], 2)
+    ny, nx = ops.core
+    tail = lambda fl: (ops.batch, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
+                       float(delx), float(delxSqr), float(ratio), float(ratioQtr), float(ratioSqr),
+                       float(optArg), float(undef), C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("gen2d", ops, tail, flags, ordering, engine, check_every, ctx, profile)
+
+
+def solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1Sqr, optArg,
+                      undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
+                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False):
+    """Batched ``invert_standard_3D`` (numbas.py:15-212) over S[..., nz, ny, nx], in place."""
+    ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("F", F)], 3)
+    nz, ny, nx = ops.core
+    tail = lambda fl: (ops.batch, nz, ny, nx, _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
+                       float(delxSqr), float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
+                       C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("std3d", ops, tail, flags, ordering, engine, check_every, ctx, profile)
+
+
+# ---------------------------------------------------------------------------
+# single-slice shims with the reference's numba signatures
+# ---------------------------------------------------------------------------
+def _store_flags(flags, fl):
+    flags[0], flags[1], flags[2] = fl[0, 0], fl[0, 1], fl[0, 2]
+
+
+def invert_standard_2D(S, A, B, C_, F, yc, xc, dely, delx, BCy, BCx, delxSqr,
+                       ratioQtr, ratioSqr, optArg, undef, flags, mxLoop, tolerance, **kw):
+    """Same positional signature as ``numbas.invert_standard_2D`` (numbas.py:216-219)."""
+    if tuple(S.shape) != (yc, xc):
+        raise ValueError(f"S.shape {tuple(S.shape)} != (yc, xc) = {(yc, xc)}")
+    fl, _ = solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg,
+                              undef, flags, mxLoop, tolerance, **kw)
+    _store_flags(flags, fl)
+    return S
+
+
+def invert_general_2D(S, A, B, C_, D, E, F, G, yc, xc, dely, delx, BCy, BCx,
+                      delxSqr, ratio, ratioQtr, ratioSqr, optArg, undef, flags,
+                      mxLoop, tolerance, **kw):
+    """Same positional signature as ``numbas.invert_general_2D`` (numbas.py:988-991)."""
+    if tuple(S.shape) != (yc, xc):
+        raise ValueError(f"S.shape {tuple(S.shape)} != (yc, xc) = {(yc, xc)}")
+    fl, _ = solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ratioQtr,
+                             ratioSqr, optArg, undef, flags, mxLoop, tolerance, **kw)
+    _store_flags(flags, fl)
+    return S
+
+
+def invert_standard_3D(S, A, B, C_, F, zc, yc, xc, delz, dely, delx, BCz, BCy, BCx,
+                       delxSqr, ratio2Sqr, ratio1Sqr, optArg, undef, flags, mxLoop,
+                       tolerance, **kw):
+    """Same positional signature as ``numbas.invert_standard_3D`` (numbas.py:16-19)."""
+    if tuple(S.shape) != (zc, yc, xc):
+        raise ValueError(f"S.shape {tuple(S.shape)} != (zc, yc, xc) = {(zc, yc, xc)}")
+    fl, _ = solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1Sqr, optArg,
+                              undef, flags, mxLoop, tolerance, **kw)
+    _store_flags(flags, fl)
+    return S
