@@ -1,0 +1,94 @@
+"""GPU parity of the TMA-fused red+black engine (XINV_ENGINE_FUSED) against the
+ordering-matched C oracle: BIT-EXACT fields, identical loop counts (same bar as
+tests/test_gpu_parity.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import xinvert_b200 as xb
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+BCS = [("fixed", "fixed"), ("fixed", "periodic"), ("extend", "fixed"), ("extend", "periodic")]
+SHAPES = [(40, 64), (33, 47), (3, 4), (28, 60), (29, 61), (57, 122), (130, 258), (200, 366)]
+
+
+def _check(c, bcy, bcx, sweeps, tol=-1.0, omega=1.4):
+    S_o, f_o = cases.run_std2d(oracle, c, bcy, bcx, sweeps, tol, omega=omega, ordering="colour")
+    S_g, f_g = cases.run_std2d(xb, c, bcy, bcx, sweeps, tol, omega=omega, engine="fused")
+    assert xb.default_context().stats()["engine"] == "fused"
+    assert np.array_equal(S_g, S_o), f"max diff {np.abs(S_g - S_o).max()} at {np.argwhere(S_g != S_o)[:5]}"
+    assert f_g[0] == f_o[0] and f_g[2] == f_o[2]
+    assert np.isclose(f_g[1], f_o[1], rtol=1e-6, atol=1e-18)
+
+
+@pytest.mark.parametrize("variant", ["0", "1"])
+@pytest.mark.parametrize("bcy,bcx", BCS)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_fused_bit_exact(gpu_ctx, monkeypatch, variant, bcy, bcx, shape):
+    monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
+    if bcx == "periodic" and shape[1] % 2:
+        pytest.skip("odd nx + periodic-x uses the wrap-fix colours (colour engine)")
+    c = cases.random_std2d(*shape, with_B=False, seed=shape[0] * 1000 + shape[1])
+    for sweeps in (0, 1, 6):
+        _check(c, bcy, bcx, sweeps)
+
+
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_fused_poisson_to_tolerance(gpu_ctx, monkeypatch, variant):
+    monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
+    c = cases.poisson_latlon(90, 180, land=True, noise=1e-6, seed=0)
+    _check(c, "extend", "periodic", 5000, tol=1e-8)
+    _check(c, "fixed", "periodic", 5000, tol=1e-8)
+
+
+def test_fused_odd_nx_periodic_falls_back_to_colour_engine(gpu_ctx):
+    c = cases.random_std2d(20, 31, with_B=False, seed=1)
+    with pytest.raises(xb.XinvError):
+        cases.run_std2d(xb, c, "fixed", "periodic", 3, -1.0, engine="fused")
+    S_o, _ = cases.run_std2d(oracle, c, "fixed", "periodic", 3, -1.0, ordering="colour")
+    S_g, _ = cases.run_std2d(xb, c, "fixed", "periodic", 3, -1.0, engine="auto")
+    assert np.array_equal(S_g, S_o)
+    assert xb.default_context().stats()["engine"] == "colour"
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_fused_batched_freeze(gpu_ctx, shared):
+    """Batch of slices with shared (stride 0) or per-slice coefficients; every slice
+    stops on its own test and equals its single-slice oracle run."""
+    B = 4
+    c = cases.poisson_latlon(60, 124, land=True, noise=1e-6, seed=2, batch=B)
+    for b in range(B):
+        c["F"][b][c["F"][b] != cases.UNDEF] *= (1.0 + 2.0 * b)
+    p = c["p"]
+    A = c["A"] if shared else np.ascontiguousarray(np.broadcast_to(c["A"], (B,) + c["A"].shape))
+    Cc = c["C"] if shared else np.ascontiguousarray(np.broadcast_to(c["C"], (B,) + c["C"].shape))
+    S = c["S0"].copy()
+    fl, st = xb.solve_standard_2D(S, A, None, Cc, c["F"], "extend", "periodic", p["del1Sqr"], p["ratioQtr"],
+                                  p["ratioSqr"], 1.4, mxLoop=3000, tolerance=1e-7, engine="fused")
+    assert st["engine"] == "fused"
+    for b in range(B):
+        cb = dict(A=c["A"], C=c["C"], F=c["F"][b], S0=c["S0"][b], p=p)
+        S_o, f_o = cases.run_std2d(oracle, cb, "extend", "periodic", 3000, 1e-7, omega=1.4, ordering="colour")
+        assert fl[b, 2] == f_o[2]
+        assert np.array_equal(S[b], S_o)
+    assert len({int(x) for x in fl[:, 2]}) > 1          # they really stopped at different sweeps
+
+
+def test_fused_device_pointers(gpu_ctx):
+    """mem_space = DEVICE: operands are CUDA tensors, S updated in place."""
+    import torch
+    c = cases.poisson_latlon(64, 120, land=True, noise=1e-6, seed=3)
+    p = c["p"]
+    dev = torch.device("cuda", 0)
+    S = torch.zeros(c["S0"].shape, dtype=torch.float64, device=dev)
+    A, Cc, F = (torch.from_numpy(c[k]).to(dev) for k in ("A", "C", "F"))
+    torch.cuda.synchronize()
+    fl, st = xb.solve_standard_2D(S, A, None, Cc, F, "fixed", "periodic", p["del1Sqr"], p["ratioQtr"],
+                                  p["ratioSqr"], 1.4, mxLoop=50, tolerance=-1.0, engine="fused")
+    S_o, f_o = cases.run_std2d(oracle, c, "fixed", "periodic", 50, -1.0, omega=1.4, ordering="colour")
+    assert st["h2d_bytes"] == 0 and st["d2h_bytes"] == 0
+    assert np.array_equal(S.cpu().numpy(), S_o)

@@ -436,10 +436,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     if (pb.ordering == XINV_ORDER_COLOUR && o.engine != XINV_ENGINE_COLOUR) {
         std::string why;
         if (fused_plan_supported(pb.kind, pb.hasB, g, why)) {
-            // the fused engine ping-pongs between two S buffers
-            if ((rc = ensure(c->stage[1], slice_bytes * a.batch))) return rc;
-            pb.dS2 = (double *)c->stage[1].p;
-            rc = fused_plan_build(pb.fused, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, pb.dS2, c->stream, why);
+            rc = fused_plan_build(pb.fused, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, nullptr, c->stream, why);
             if (rc == 0) pb.engine = XINV_ENGINE_FUSED;
             else if (o.engine == XINV_ENGINE_FUSED)
                 return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
@@ -559,10 +556,12 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
             rc = lex_sweep(c->stream, pb.kind, pb.hasB, pb.g, pb.q, pb.batch, pb.dS, (XdSliceState *)c->state.p,
                            pb.nblk_norm, (double *)c->psum.p, (i64 *)c->pcnt.p, (unsigned *)c->ticket.p,
                            (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
-        else if (pb.engine == XINV_ENGINE_FUSED)
+        else if (pb.engine == XINV_ENGINE_FUSED) {
+            prof_mark(c, pb);
             rc = fused_sweep(pb.fused, c->stream, (XdSliceState *)c->state.p, (double *)c->psum.p, (i64 *)c->pcnt.p,
-                             (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
-        else
+                             (unsigned *)c->ticket.p, (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
+            prof_mark(c, pb);
+        } else
             rc = sweep_colour_engine(c, pb);
         if (rc) return rc;
     }
@@ -583,16 +582,6 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
     return XINV_OK;
 }
 
-// gather per-slice results of the ping-pong engine into dS
-__global__ void xd_gather_pingpong_kernel(double *__restrict__ dst, const double *__restrict__ other,
-                                          i64 N, const XdSliceState *__restrict__ st)
-{
-    const int b = blockIdx.y;
-    if ((st[b].sweeps_done & 1) == 0) return;       // even number of sweeps: result already in dst
-    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < N) dst[(i64)b * N + p] = other[(i64)b * N + p];
-}
-
 extern "C" int xinv_end(xinv_ctx *c)
 {
     if (!c) return set_err(XINV_E_ARG, "ctx is NULL");
@@ -603,8 +592,7 @@ extern "C" int xinv_end(xinv_ctx *c)
     if (pb.batch == 0) return XINV_OK;
     const XdGeom &g = pb.g;
     if (pb.engine == XINV_ENGINE_FUSED) {
-        dim3 grid((unsigned)((g.N + 255) / 256), (unsigned)pb.batch);
-        xd_gather_pingpong_kernel<<<grid, 256, 0, c->stream>>>(pb.dS, pb.dS2, g.N, (const XdSliceState *)c->state.p);
+        fused_unpack(pb.fused, pb.dS, (const XdSliceState *)c->state.p, c->stream);
         c->stats.kernel_launches++;
         CK(cudaGetLastError());
     }
@@ -629,6 +617,7 @@ extern "C" int xinv_end(xinv_ctx *c)
     }
     c->stats.cell_updates = updates;
     c->stats.sweep_ms = pb.sweeps_launched ? c->stats.solve_ms / (double)pb.sweeps_launched : 0.0;
+    fused_plan_release(pb.fused);
     return XINV_OK;
 }
 
