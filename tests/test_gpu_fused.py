@@ -1,6 +1,10 @@
-"""GPU parity of the TMA-fused red+black engine (XINV_ENGINE_FUSED) against the
-ordering-matched C oracle: BIT-EXACT fields, identical loop counts (same bar as
-tests/test_gpu_parity.py)."""
+"""GPU parity of the TMA-fed warp-marching engine (XINV_ENGINE_FUSED; T = 1 or 2
+red+black iterations per pass) against the ordering-matched C oracle: BIT-EXACT
+fields, identical loop counts (same bar as tests/test_gpu_parity.py).
+
+XINV_FUSED_VARIANT selects the kernel instantiation (T, rows per TMA chunk, ring
+depth, CTAs/SM; xinv_march2d.cuh: XM_VARIANTS), XINV_FUSED_RB forces the owned rows
+per strip so that small grids are cut into many strips."""
 import os
 
 import numpy as np
@@ -25,7 +29,10 @@ def _check(c, bcy, bcx, sweeps, tol=-1.0, omega=1.4):
     assert np.isclose(f_g[1], f_o[1], rtol=1e-6, atol=1e-18)
 
 
-@pytest.mark.parametrize("variant", ["0", "1"])
+VARIANTS = ["0", "1", "2", "3", "4", "5"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("bcy,bcx", BCS)
 @pytest.mark.parametrize("shape", SHAPES)
 def test_fused_bit_exact(gpu_ctx, monkeypatch, variant, bcy, bcx, shape):
@@ -33,16 +40,50 @@ def test_fused_bit_exact(gpu_ctx, monkeypatch, variant, bcy, bcx, shape):
     if bcx == "periodic" and shape[1] % 2:
         pytest.skip("odd nx + periodic-x uses the wrap-fix colours (colour engine)")
     c = cases.random_std2d(*shape, with_B=False, seed=shape[0] * 1000 + shape[1])
-    for sweeps in (0, 1, 6):
+    for sweeps in (0, 1, 2, 6, 7):          # mxLoop: 1, 2, 3, 7, 8 sweeps (odd counts end a T=2 solve on a 1-iteration pass)
         _check(c, bcy, bcx, sweeps)
 
 
-@pytest.mark.parametrize("variant", ["0", "1"])
+@pytest.mark.parametrize("variant", ["0", "2", "5"])
+@pytest.mark.parametrize("rb", ["1", "3", "8", "17"])
+@pytest.mark.parametrize("bcy,bcx", BCS)
+def test_fused_many_strips(gpu_ctx, monkeypatch, variant, rb, bcy, bcx):
+    """Force tiny strips: every strip boundary (rows and columns) falls inside the grid."""
+    monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
+    monkeypatch.setenv("XINV_FUSED_RB", rb)
+    for shape in [(41, 130), (64, 256)]:
+        c = cases.random_std2d(*shape, with_B=False, seed=shape[0] + 7 * shape[1])
+        for sweeps in (0, 4, 5):
+            _check(c, bcy, bcx, sweeps)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_fused_poisson_to_tolerance(gpu_ctx, monkeypatch, variant):
     monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
     c = cases.poisson_latlon(90, 180, land=True, noise=1e-6, seed=0)
     _check(c, "extend", "periodic", 5000, tol=1e-8)
     _check(c, "fixed", "periodic", 5000, tol=1e-8)
+
+
+@pytest.mark.parametrize("variant", ["2", "3", "5"])
+def test_fused_t2_redo_when_stopping_mid_pass(gpu_ctx, monkeypatch, variant):
+    """T = 2: tolerances chosen so that the stop test fires after the 1st and after the
+    2nd iteration of a pass (even and odd sweep counts); the overshoot is rolled back."""
+    monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
+    c = cases.poisson_latlon(60, 120, land=True, noise=1e-6, seed=5)
+    seen = set()
+    for tol in (3e-3, 2e-3, 1e-3, 7e-4, 5e-4, 3e-4, 2e-4, 1e-4, 5e-5):
+        S_o, f_o = cases.run_std2d(oracle, c, "fixed", "periodic", 5000, tol, omega=1.4, ordering="colour")
+        S_g, f_g = cases.run_std2d(xb, c, "fixed", "periodic", 5000, tol, omega=1.4, engine="fused")
+        assert f_g[2] == f_o[2] and np.array_equal(S_g, S_o), (tol, f_g, f_o)
+        seen.add(int(f_o[2]) & 1)
+    assert seen == {0, 1}
+    # overflow in the first iteration of a pass
+    c = cases.random_std2d(30, 40, with_B=False, seed=9)
+    S_o, f_o = cases.run_std2d(oracle, c, "fixed", "fixed", 5000, 1e-12, omega=7.0, ordering="colour")
+    S_g, f_g = cases.run_std2d(xb, c, "fixed", "fixed", 5000, 1e-12, omega=7.0, engine="fused")
+    assert f_o[0] == 1 and f_g[0] == 1 and f_g[2] == f_o[2]
+    assert np.array_equal(S_g, S_o, equal_nan=True)
 
 
 def test_fused_odd_nx_periodic_falls_back_to_colour_engine(gpu_ctx):
@@ -92,3 +133,20 @@ def test_fused_device_pointers(gpu_ctx):
     S_o, f_o = cases.run_std2d(oracle, c, "fixed", "periodic", 50, -1.0, omega=1.4, ordering="colour")
     assert st["h2d_bytes"] == 0 and st["d2h_bytes"] == 0
     assert np.array_equal(S.cpu().numpy(), S_o)
+
+
+@pytest.mark.parametrize("variant", ["1", "3"])
+def test_fused_plain_division_fallback(gpu_ctx, monkeypatch, variant):
+    """Coefficients of order 1e306 put the denominators outside the range the fast
+    division accepts: the strips are redone with the plain division and the result
+    stays bit-equal to the oracle; ordinary inputs never take that path."""
+    monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
+    c = cases.random_std2d(40, 64, with_B=False, seed=77)
+    _check(c, "fixed", "periodic", 6)
+    assert xb.default_context().stats()["slow_strips"] == 0
+    big = dict(c, A=c["A"] * 1e306, C=c["C"] * 1e306, F=np.where(c["F"] == cases.UNDEF, cases.UNDEF, c["F"] * 1e306))
+    S_o, f_o = cases.run_std2d(oracle, big, "fixed", "periodic", 6, -1.0, omega=1.4, ordering="colour")
+    S_g, f_g = cases.run_std2d(xb, big, "fixed", "periodic", 6, -1.0, omega=1.4, engine="fused")
+    assert xb.default_context().stats()["slow_strips"] > 0
+    assert np.isfinite(S_o).all()
+    assert np.array_equal(S_g, S_o) and f_g[2] == f_o[2]

@@ -21,7 +21,7 @@
 #include "../../include/xinv.h"
 #include "xinv_device.cuh"
 #include "xinv_colour_engine.cuh"
-#include "xinv_fused2d.cuh"
+#include "xinv_march2d.cuh"
 #include "xinv_lex_engine.cuh"
 
 // ---------------------------------------------------------------------------
@@ -91,6 +91,7 @@ struct xinv_ctx {
     // workspace (grown on demand, reused across calls)
     DevBuf stage[10];            // staged S, S2 and up to 8 coefficient arrays
     DevBuf state, psum, pcnt, ticket, nactive;
+    XmWork xm_work;              // padded operand copies of the fused engine
     int *h_nactive_pinned = nullptr;
     Problem pb;
     xinv_stats stats{};
@@ -179,6 +180,7 @@ extern "C" void xinv_destroy(xinv_ctx *c)
     release(c->state); release(c->psum); release(c->pcnt); release(c->ticket); release(c->nactive);
     release(c->nccl_buf);
     fused_plan_release(c->pb.fused);
+    xm_work_release(c->xm_work);
     if (c->h_nactive_pinned) cudaFreeHost(c->h_nactive_pinned);
     for (auto e : c->prof_ev) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -269,10 +271,10 @@ extern "C" int xinv_memcpy_d2h(xinv_ctx *c, void *dst, const void *src, int64_t 
 // ---------------------------------------------------------------------------
 // begin: validate, stage, initialise per-slice state
 // ---------------------------------------------------------------------------
-__global__ void xd_init_state_kernel(XdSliceState *st, const double *flags_in, int batch, int *nactive)
+__global__ void xd_init_state_kernel(XdSliceState *st, const double *flags_in, int batch, int *nactive, int nit0)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0) *nactive = batch;
+    if (b == 0) { nactive[0] = batch; nactive[1] = 0; }
     if (b >= batch) return;
     XdSliceState s;
     s.normPrev = DBL_MAX;                  // numbas.py:280 np.finfo(np.float64).max
@@ -282,6 +284,10 @@ __global__ void xd_init_state_kernel(XdSliceState *st, const double *flags_in, i
     s.loop = 0;
     s.active = 1;
     s.sweeps_done = 0;
+    s.cur = 0;
+    s.nit = nit0;
+    s.redo = 0;
+    s.pad_ = 0;
     st[b] = s;
 }
 
@@ -402,23 +408,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
         }
     }
 
-    // ---- per-slice state ----------------------------------------------------
     int rc;
-    if ((rc = ensure(c->state, sizeof(XdSliceState) * a.batch))) return rc;
-    if ((rc = ensure(c->nactive, 64))) return rc;
-    if ((rc = ensure(c->ticket, sizeof(unsigned) * a.batch))) return rc;
-    // flags in -> device (reuse psum buffer temporarily is awkward; use a small staging alloc)
-    DevBuf ftmp;
-    if ((rc = ensure(ftmp, sizeof(double) * 3 * a.batch))) return rc;
-    CK(cudaMemcpyAsync(ftmp.p, a.flags, sizeof(double) * 3 * a.batch, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->ticket.p, 0, sizeof(unsigned) * a.batch, c->stream));
-    xd_init_state_kernel<<<(unsigned)((a.batch + 127) / 128), 128, 0, c->stream>>>(
-        (XdSliceState *)c->state.p, (const double *)ftmp.p, (int)a.batch, (int *)c->nactive.p);
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));
-    release(ftmp);
-    pb.h_nactive = (int)a.batch;
-
     // norm partial layout: enough blocks to fill the machine, few enough that the
     // last-block pass stays trivial
     {
@@ -436,7 +426,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     if (pb.ordering == XINV_ORDER_COLOUR && o.engine != XINV_ENGINE_COLOUR) {
         std::string why;
         if (fused_plan_supported(pb.kind, pb.hasB, g, why)) {
-            rc = fused_plan_build(pb.fused, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, nullptr, c->stream, why);
+            rc = fused_plan_build(pb.fused, c->xm_work, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, pb.mxLoop, c->stream, why);
             if (rc == 0) pb.engine = XINV_ENGINE_FUSED;
             else if (o.engine == XINV_ENGINE_FUSED)
                 return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
@@ -450,7 +440,27 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
         if ((rc = ensure(c->psum, sizeof(double) * a.batch * np))) return rc;
         if ((rc = ensure(c->pcnt, sizeof(i64) * a.batch * np))) return rc;
     }
+    // ---- per-slice state ----------------------------------------------------
+    if ((rc = ensure(c->state, sizeof(XdSliceState) * a.batch))) return rc;
+    if ((rc = ensure(c->nactive, 64))) return rc;
+    if ((rc = ensure(c->ticket, sizeof(unsigned) * a.batch))) return rc;
+    // flags in -> device (reuse psum buffer temporarily is awkward; use a small staging alloc)
+    DevBuf ftmp;
+    if ((rc = ensure(ftmp, sizeof(double) * 3 * a.batch))) return rc;
+    CK(cudaMemcpyAsync(ftmp.p, a.flags, sizeof(double) * 3 * a.batch, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->ticket.p, 0, sizeof(unsigned) * a.batch, c->stream));
+    {
+        const int nit0 = (pb.engine == XINV_ENGINE_FUSED && pb.fused.T > 1 && a.mxLoop >= 1) ? pb.fused.T : 1;
+        xd_init_state_kernel<<<(unsigned)((a.batch + 127) / 128), 128, 0, c->stream>>>(
+            (XdSliceState *)c->state.p, (const double *)ftmp.p, (int)a.batch, (int *)c->nactive.p, nit0);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    release(ftmp);
+    pb.h_nactive = (int)a.batch;
+
     c->stats.engine = pb.engine;
+    c->stats.iters_per_pass = (pb.engine == XINV_ENGINE_FUSED) ? pb.fused.T : 1;
     pb.open = true;
     return XINV_OK;
 }
@@ -546,7 +556,10 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
     if (!pb.open) return set_err(XINV_E_STATE, "no open problem (call xinv_*_begin first)");
     CK(cudaSetDevice(c->device));
     if (pb.batch == 0 || pb.h_nactive == 0) { if (n_active_out) *n_active_out = 0; return XINV_OK; }
-    const i64 remaining = (pb.mxLoop + 1) - pb.sweeps_launched;   // at most mxLoop+1 sweeps (numbas.py:410)
+    // a pass (launch) performs >= 1 sweep on every active slice, except for at most one
+    // "redo" pass per slice (fused engine, T > 1): at most mxLoop + 2 passes (numbas.py:410)
+    const i64 max_passes = pb.mxLoop + 1 + ((pb.engine == XINV_ENGINE_FUSED && pb.fused.T > 1) ? 1 : 0);
+    const i64 remaining = max_passes - pb.sweeps_launched;
     if (sweeps <= 0) sweeps = auto_check_every(c, pb);
     if (sweeps > remaining) sweeps = remaining;
     CK(cudaEventRecord(c->ev0, c->stream));
@@ -567,7 +580,7 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
     }
     pb.sweeps_launched += sweeps;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_nactive_pinned, c->nactive.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_nactive_pinned, c->nactive.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0;
@@ -575,9 +588,11 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
     c->stats.solve_ms += ms;
     if (pb.profile) prof_collect(c, pb.engine == XINV_ENGINE_FUSED ? 1 : pb.g.ncol);
     c->stats.sweeps_launched = pb.sweeps_launched;
-    pb.h_nactive = *c->h_nactive_pinned;
-    if (pb.h_nactive != 0 && pb.sweeps_launched >= pb.mxLoop + 1)
-        return set_err(XINV_E_STATE, "internal error: %d slices still active after mxLoop+1 sweeps", pb.h_nactive);
+    pb.h_nactive = c->h_nactive_pinned[0];
+    c->stats.slow_strips = c->h_nactive_pinned[1];
+    if (pb.h_nactive != 0 && pb.sweeps_launched >= max_passes)
+        return set_err(XINV_E_STATE, "internal error: %d slices still active after %lld passes", pb.h_nactive,
+                       (long long)max_passes);
     if (n_active_out) *n_active_out = pb.h_nactive;
     return XINV_OK;
 }
@@ -609,14 +624,16 @@ extern "C" int xinv_end(xinv_ctx *c)
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->stats.d2h_ms = ms;
     i64 updates = 0;
+    int max_done = 0;
     for (i64 b = 0; b < pb.batch; ++b) {
+        if (hs[b].sweeps_done > max_done) max_done = hs[b].sweeps_done;
         pb.userFlags[3 * b + 0] = hs[b].flags[0];
         pb.userFlags[3 * b + 1] = hs[b].flags[1];
         pb.userFlags[3 * b + 2] = hs[b].flags[2];
         updates += (i64)hs[b].sweeps_done * g.N;
     }
     c->stats.cell_updates = updates;
-    c->stats.sweep_ms = pb.sweeps_launched ? c->stats.solve_ms / (double)pb.sweeps_launched : 0.0;
+    c->stats.sweep_ms = max_done ? c->stats.solve_ms / (double)max_done : 0.0;
     fused_plan_release(pb.fused);
     return XINV_OK;
 }

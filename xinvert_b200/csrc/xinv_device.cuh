@@ -191,6 +191,11 @@ struct XdSliceState {
     i64    loop;
     int    active;
     int    sweeps_done;   // sweeps actually executed on this slice
+    // fused engine only (xinv_march2d.cuh):
+    int    cur;           // which ping-pong buffer holds the slice's current psi
+    int    nit;           // iterations the next pass runs on this slice (1..T)
+    int    redo;          // next pass re-runs the final iteration(s); loop control already done
+    int    pad_;
 };
 
 // Loop control of the reference after each sweep: numbas.py:401-414 (2-D
