@@ -1,0 +1,153 @@
+"""GPU: the xarray-in / xarray-out facade end to end through the C-ABI.
+
+* reference known answers (tests/test_GillMatsuno.py:55-57 of the reference; SURVEY.md
+  section 4 probes) with ``ordering='lexicographic'``: the reference's own trajectory,
+  so loop counts and values must match to 1e-12 relative;
+* the default red-black ordering against the same goldens at the reference tests' own
+  tolerance (np.isclose default, rtol 1e-5) and against the ordering-matched oracle
+  (bit-exact) on the BASELINE-shaped problems C1, C3, C4.
+"""
+import numpy as np
+import pytest
+
+import oracle
+import xinvert_b200 as xb
+from xinvert_b200 import core
+from tests import oracle_backend
+from tests.test_apps_host import _c1_zeta, _grid2
+
+pytestmark = pytest.mark.gpu
+DA = xb.DataArray
+
+
+def _gm_inputs():
+    lon, lat = np.linspace(0, 360, 144), np.linspace(-90, 90, 73)
+    la, lo, coords = _grid2(73, 144, lat, lon)
+    Q1 = 0.05 * np.exp(-((la - 0) ** 2 + (lo - 120) ** 2) / 100.0)
+    Q2 = 0.05 * np.exp(-((la - 10) ** 2 + (lo - 120) ** 2) / 100.0) - 0.05 * np.exp(-((la + 10) ** 2 + (lo - 120) ** 2) / 100.0)
+    Q3 = 0.05 * np.exp(-((la - 10) ** 2 + (lo - 120) ** 2) / 100.0)
+    return np.stack([Q1, Q2, Q3]), coords
+
+
+def test_gill_matsuno_reference_golden_lexicographic(gpu_ctx, capsys):
+    """All three heatings as ONE batched call (a 'case' dim), reference ordering."""
+    Q, coords = _gm_inputs()
+    iParams = {'BCs': ['fixed', 'periodic'], 'mxLoop': 2000, 'tolerance': 1e-8, 'optArg': 1.4,
+               'ordering': 'lexicographic'}
+    mParams = {'epsilon': 1e-5, 'Phi': 5000}
+    h = xb.invert_GillMatsuno(DA(Q, ['case', 'lat', 'lon'], dict(coords, case=np.arange(3))), dims=['lat', 'lon'],
+                              iParams=iParams, mParams=mParams)
+    out = capsys.readouterr().out
+    for loops in (1628, 1146, 1618):
+        assert f"loops {loops:4.0f} and tolerance is" in out
+    u, v = xb.cal_flow(h, dims=['lat', 'lon'], BCs=['fixed', 'periodic'], mParams=mParams, vtype='GillMatsuno')
+    ke = ((u.values ** 2 + v.values ** 2) / 2).sum(axis=(1, 2))
+    assert np.allclose(ke, [4351.62244687, 5833.33192343, 5100.85325027], rtol=1e-10, atol=0)
+
+
+def test_gill_matsuno_reference_golden_default_ordering(gpu_ctx):
+    """Default (red-black) ordering: the reference test's own assertions hold."""
+    Q, coords = _gm_inputs()
+    iParams = {'BCs': ['fixed', 'periodic'], 'mxLoop': 2000, 'tolerance': 1e-8, 'optArg': 1.4, 'printInfo': False}
+    mParams = {'epsilon': 1e-5, 'Phi': 5000}
+    h = xb.invert_GillMatsuno(DA(Q, ['case', 'lat', 'lon'], dict(coords, case=np.arange(3))), dims=['lat', 'lon'],
+                              iParams=iParams, mParams=mParams)
+    u, v = xb.cal_flow(h, dims=['lat', 'lon'], BCs=['fixed', 'periodic'], mParams=mParams, vtype='GillMatsuno')
+    ke = ((u.values ** 2 + v.values ** 2) / 2).sum(axis=(1, 2))
+    assert (h.values[0] <= 0).all() and (np.abs(h.values[1]) <= 370).all() and (h.values[2] <= 0).all()
+    assert np.isclose(ke[0], 4351.62244687) and np.isclose(ke[1], 5833.33192343) and np.isclose(ke[2], 5100.85325027)
+
+
+def test_poisson_c1_reference_known_answer(gpu_ctx, capsys):
+    """BASELINE configs[0]: lexicographic order reproduces the reference run exactly
+    (loop 2380, max|psi| 13182413.993245527); the default order converges to the same
+    field within the iteration tolerance and in a comparable number of sweeps."""
+    zeta, coords = _c1_zeta()
+    ip = {'BCs': ['fixed', 'periodic'], 'optArg': 1.4, 'tolerance': 1e-8, 'mxLoop': 5000}
+    F = DA(zeta, ['lat', 'lon'], coords)
+    lex = xb.invert_Poisson(F, dims=['lat', 'lon'], iParams=dict(ip, ordering='lexicographic'))
+    assert "loops 2380" in capsys.readouterr().out
+    assert np.isclose(np.abs(lex.values).max(), 13182413.993245527, rtol=1e-12)
+    rb = xb.invert_Poisson(F, dims=['lat', 'lon'], iParams=ip)
+    loops = int(capsys.readouterr().out.split("loops")[1].split()[0])
+    assert 1500 < loops < 3500
+    assert np.abs(rb.values - lex.values).max() / np.abs(lex.values).max() < 1e-4
+
+
+def _via_oracle(fn, *a, **k):
+    """Same facade call with the C oracle as the backend (host logic identical)."""
+    saved = core.solvers
+    core.solvers = oracle_backend
+    try:
+        return fn(*a, **k)
+    finally:
+        core.solvers = saved
+
+
+def test_c3_omega_3d_bit_exact_vs_oracle(gpu_ctx):
+    """BASELINE configs[2] shape at reduced size in y/x (the oracle must finish in seconds):
+    37 levels, variable N2(lev,lat,lon), fixed/fixed/periodic."""
+    nz, ny, nx = 37, 60, 120
+    lev = 100000.0 - 2500.0 * np.arange(nz)
+    lat = -88.5 + 3.0 * np.arange(ny)
+    lon = 3.0 * np.arange(nx)
+    rng = np.random.default_rng(1)
+    coords = {'LEV': lev, 'lat': lat, 'lon': lon}
+    N2 = DA(1e-6 * (1 + 0.5 * rng.random((nz, ny, nx))), ['LEV', 'lat', 'lon'], coords)
+    F = DA(1e-17 * rng.standard_normal((nz, ny, nx)), ['LEV', 'lat', 'lon'], coords)
+    ip = {'BCs': ['fixed', 'fixed', 'periodic'], 'tolerance': 1e-10, 'mxLoop': 60, 'printInfo': False}
+    kw = dict(dims=['LEV', 'lat', 'lon'], iParams=ip, mParams={'N2': N2})
+    w_g = xb.invert_omega(F, **kw)
+    w_o = _via_oracle(xb.invert_omega, F, **kw)
+    assert np.array_equal(w_g.values, w_o.values)
+
+
+def test_c4_gill_matsuno_beta_plane_bit_exact_vs_oracle(gpu_ctx):
+    """BASELINE configs[3]: 720x360 cartesian beta-plane (SURVEY.md 8d recipe), 150 sweeps."""
+    ny, nx = 360, 720
+    y = np.linspace(-5e6, 5e6, ny)
+    x = np.linspace(0, 4e7, nx, endpoint=False)
+    yy, xx, coords = _grid2(ny, nx, y, x, 'y', 'x')
+    Q = DA(0.05 * np.exp(-((yy / 1e6) ** 2 + ((xx - 2e7) / 2e6) ** 2)), ['y', 'x'], coords)
+    ip = {'BCs': ['fixed', 'periodic'], 'optArg': 1.4, 'tolerance': -1.0, 'mxLoop': 149, 'printInfo': False}
+    mp = {'f0': 0.0, 'beta': 2e-11, 'epsilon': 1e-5, 'Phi': 5000}
+    kw = dict(dims=['y', 'x'], coords='cartesian', iParams=ip, mParams=mp)
+    h_g = xb.invert_GillMatsuno(Q, **kw)
+    h_o = _via_oracle(xb.invert_GillMatsuno, Q, **kw)
+    assert np.array_equal(h_g.values, h_o.values) and np.abs(h_g.values).max() > 0
+    u, v = xb.cal_flow(h_g, dims=['y', 'x'], coords='cartesian', mParams=mp, vtype='GillMatsuno')
+    assert np.isfinite(u.values).all() and np.isfinite(v.values).all()
+
+
+def test_c2_style_ocean_poisson_batched(gpu_ctx, capsys):
+    """Helmholtz_ocean-style (tests/test_Poisson.py:44-65 of the reference): land mask,
+    extend/periodic, several time slices; fused engine; each slice equals the oracle."""
+    ny, nx, T = 90, 180, 4
+    zeta, coords = _c1_zeta(ny, nx)
+    rng = np.random.default_rng(0)
+    z = np.stack([zeta * (1 + 0.5 * t) + 1e-6 * rng.standard_normal((ny, nx)) for t in range(T)])
+    lam, phi = np.deg2rad(coords['lon'])[None, :], np.deg2rad(coords['lat'])[:, None]
+    z[:, np.sin(5 * lam) * np.cos(3 * phi) > 0.6] = np.nan
+    F = DA(z, ['time', 'lat', 'lon'], dict(coords, time=np.arange(T)))
+    ip = {'BCs': ['extend', 'periodic'], 'tolerance': 1e-9, 'mxLoop': 5000}
+    s_g = xb.invert_Poisson(F, dims=['lat', 'lon'], iParams=ip)
+    out_g = capsys.readouterr().out
+    assert xb.default_context().stats()["engine"] == "fused"
+    s_o = _via_oracle(xb.invert_Poisson, F, dims=['lat', 'lon'], iParams=ip)
+    out_o = capsys.readouterr().out
+    assert np.array_equal(s_g.values, s_o.values, equal_nan=True)
+    loops = lambda txt: [ln.split("loops")[1].split()[0] for ln in txt.strip().splitlines()]
+    assert loops(out_g) == loops(out_o)
+
+
+def test_linearity_property(gpu_ctx):
+    """tests/test_Geopotential.py:92-104 of the reference, on synthetic data:
+    invert(F1 + F2) == invert(F1) + invert(F2) to 5e-5 relative."""
+    zeta, coords = _c1_zeta(60, 120)
+    rng = np.random.default_rng(4)
+    F1 = zeta
+    F2 = 1e-5 * rng.standard_normal(zeta.shape) * np.cos(np.deg2rad(coords['lat']))[:, None]
+    ip = {'BCs': ['fixed', 'periodic'], 'tolerance': 1e-12, 'mxLoop': 8000, 'printInfo': False}
+    inv = lambda f: xb.invert_Poisson(DA(f, ['lat', 'lon'], coords), dims=['lat', 'lon'], iParams=ip).values
+    s12, s1, s2 = inv(F1 + F2), inv(F1), inv(F2)
+    assert np.allclose(s12, s1 + s2, rtol=5e-5, atol=5e-5 * np.abs(s12).max())
