@@ -93,7 +93,7 @@ typedef struct xinv_stats {
     double  sweep_ms;         /* mean device time of one full sweep (all colours)        */
     double  dom_ms;           /* opts.profile: summed device time of the dominant kernels */
     int64_t dom_launches;     /*               ... and how many launches that covers      */
-    int64_t slow_strips;      /* fused engine: strips redone with the plain division      */
+    int64_t slow_strips;      /* reserved (always 0)                                      */
     int32_t iters_per_pass;   /* fused engine: SOR iterations per pass over HBM (T)       */
     int32_t pad_;
 } xinv_stats;

@@ -29,7 +29,7 @@ def _check(c, bcy, bcx, sweeps, tol=-1.0, omega=1.4):
     assert np.isclose(f_g[1], f_o[1], rtol=1e-6, atol=1e-18)
 
 
-VARIANTS = ["0", "1", "2", "3", "4", "5"]
+VARIANTS = ["0", "1", "2", "3", "4", "5", "6"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -135,18 +135,16 @@ def test_fused_device_pointers(gpu_ctx):
     assert np.array_equal(S.cpu().numpy(), S_o)
 
 
-@pytest.mark.parametrize("variant", ["1", "3"])
-def test_fused_plain_division_fallback(gpu_ctx, monkeypatch, variant):
-    """Coefficients of order 1e306 put the denominators outside the range the fast
-    division accepts: the strips are redone with the plain division and the result
-    stays bit-equal to the oracle; ordinary inputs never take that path."""
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_fused_extreme_denominators(gpu_ctx, monkeypatch, variant):
+    """Coefficients of order 1e306 put the denominators of optArg / den at the edge of the
+    double range (quotients near the denormal boundary): the precomputed factor array must
+    still be the correctly rounded quotient the oracle forms in every sweep."""
     monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
     c = cases.random_std2d(40, 64, with_B=False, seed=77)
     _check(c, "fixed", "periodic", 6)
-    assert xb.default_context().stats()["slow_strips"] == 0
     big = dict(c, A=c["A"] * 1e306, C=c["C"] * 1e306, F=np.where(c["F"] == cases.UNDEF, cases.UNDEF, c["F"] * 1e306))
     S_o, f_o = cases.run_std2d(oracle, big, "fixed", "periodic", 6, -1.0, omega=1.4, ordering="colour")
     S_g, f_g = cases.run_std2d(xb, big, "fixed", "periodic", 6, -1.0, omega=1.4, engine="fused")
-    assert xb.default_context().stats()["slow_strips"] > 0
     assert np.isfinite(S_o).all()
     assert np.array_equal(S_g, S_o) and f_g[2] == f_o[2]
