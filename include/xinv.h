@@ -95,7 +95,7 @@ typedef struct xinv_stats {
     int64_t dom_launches;     /*               ... and how many launches that covers      */
     int64_t slow_strips;      /* reserved (always 0)                                      */
     int32_t iters_per_pass;   /* fused engine: SOR iterations per pass over HBM (T)       */
-    int32_t pad_;
+    int32_t row_coeffs;       /* fused engine: 1 = A and C were constant along x (RC kernels) */
 } xinv_stats;
 
 /* ---- context ---------------------------------------------------------- */

@@ -63,6 +63,21 @@ def random_std2d(ny, nx, with_B, seed, land=0.1, batch=None):
     return dict(A=A, B=B, C=C, F=F, S0=S0, p=p)
 
 
+def random_std2d_rowcoef(ny, nx, seed, land=0.1, batch=None, undef_rows=False):
+    """Like random_std2d (B == 0) but A and C vary with y only -- the structure every
+    Poisson-type problem has -- which selects the fused engine's RC kernels."""
+    c = random_std2d(ny, nx, False, seed, land=land, batch=batch)
+    rng = np.random.default_rng(seed + 12345)
+    a = 1.0 + 0.3 * rng.random(ny)
+    cc = 1.0 + 0.3 * rng.random(ny)
+    if undef_rows and ny > 8:
+        a[ny // 3] = UNDEF                   # a whole row of undef A: rows ny//3-1 and ny//3 are never updated
+        cc[2 * ny // 3] = UNDEF
+    c["A"] = np.ascontiguousarray(np.broadcast_to(a[:, None], (ny, nx)))
+    c["C"] = np.ascontiguousarray(np.broadcast_to(cc[:, None], (ny, nx)))
+    return c
+
+
 def random_gen2d(ny, nx, with_B, seed, land=0.1, batch=None):
     rng = np.random.default_rng(seed)
     shape = (ny, nx) if batch is None else (batch, ny, nx)

@@ -2,9 +2,11 @@
 red+black iterations per pass) against the ordering-matched C oracle: BIT-EXACT
 fields, identical loop counts (same bar as tests/test_gpu_parity.py).
 
-XINV_FUSED_VARIANT selects the kernel instantiation (T, rows per TMA chunk, ring
-depth, CTAs/SM; xinv_march2d.cuh: XM_VARIANTS), XINV_FUSED_RB forces the owned rows
-per strip so that small grids are cut into many strips."""
+Two kernel families: the general one (A, C vary in x and y; XINV_FUSED_VARIANT picks
+the instantiation: T, rows per TMA chunk, ring depth, CTAs/SM -- xinv_march2d.cuh:
+XM_VARIANTS) and the RC one, chosen automatically when A and C are constant along x
+(XINV_FUSED_RC_VARIANT; XINV_FUSED_RC=0 forces the general kernels).  XINV_FUSED_RB
+forces the owned rows per strip so that small grids are cut into many strips."""
 import os
 
 import numpy as np
@@ -20,56 +22,90 @@ BCS = [("fixed", "fixed"), ("fixed", "periodic"), ("extend", "fixed"), ("extend"
 SHAPES = [(40, 64), (33, 47), (3, 4), (28, 60), (29, 61), (57, 122), (130, 258), (200, 366)]
 
 
-def _check(c, bcy, bcx, sweeps, tol=-1.0, omega=1.4):
+def _check(c, bcy, bcx, sweeps, tol=-1.0, omega=1.4, rc=None):
     S_o, f_o = cases.run_std2d(oracle, c, bcy, bcx, sweeps, tol, omega=omega, ordering="colour")
     S_g, f_g = cases.run_std2d(xb, c, bcy, bcx, sweeps, tol, omega=omega, engine="fused")
-    assert xb.default_context().stats()["engine"] == "fused"
+    st = xb.default_context().stats()
+    assert st["engine"] == "fused"
+    if rc is not None:
+        assert st["row_coeffs"] == int(rc)
     assert np.array_equal(S_g, S_o), f"max diff {np.abs(S_g - S_o).max()} at {np.argwhere(S_g != S_o)[:5]}"
     assert f_g[0] == f_o[0] and f_g[2] == f_o[2]
     assert np.isclose(f_g[1], f_o[1], rtol=1e-6, atol=1e-18)
 
 
-VARIANTS = ["0", "1", "2", "3", "4", "5", "6"]
+VARIANTS = ["0", "1", "2", "3", "4"]          # both tables have five entries
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("bcy,bcx", BCS)
 @pytest.mark.parametrize("shape", SHAPES)
 def test_fused_bit_exact(gpu_ctx, monkeypatch, variant, bcy, bcx, shape):
+    """General kernels: A and C vary in x and y."""
     monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
     if bcx == "periodic" and shape[1] % 2:
         pytest.skip("odd nx + periodic-x uses the wrap-fix colours (colour engine)")
     c = cases.random_std2d(*shape, with_B=False, seed=shape[0] * 1000 + shape[1])
     for sweeps in (0, 1, 2, 6, 7):          # mxLoop: 1, 2, 3, 7, 8 sweeps (odd counts end a T=2 solve on a 1-iteration pass)
-        _check(c, bcy, bcx, sweeps)
+        _check(c, bcy, bcx, sweeps, rc=False)
 
 
-@pytest.mark.parametrize("variant", ["0", "2", "5"])
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("bcy,bcx", BCS)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_fused_rowcoef_bit_exact(gpu_ctx, monkeypatch, variant, bcy, bcx, shape):
+    """RC kernels: A and C constant along x (incl. whole rows of undef coefficients)."""
+    monkeypatch.setenv("XINV_FUSED_RC_VARIANT", variant)
+    if bcx == "periodic" and shape[1] % 2:
+        pytest.skip("odd nx + periodic-x uses the wrap-fix colours (colour engine)")
+    c = cases.random_std2d_rowcoef(*shape, seed=shape[0] * 1000 + shape[1] + 1, undef_rows=True)
+    for sweeps in (0, 1, 2, 6, 7):
+        _check(c, bcy, bcx, sweeps, rc=True)
+
+
+def test_fused_rowcoef_equals_general_kernels(gpu_ctx, monkeypatch):
+    """The same row-constant problem through the general kernels (XINV_FUSED_RC=0)."""
+    c = cases.random_std2d_rowcoef(57, 122, seed=4)
+    _check(c, "extend", "periodic", 7, rc=True)
+    monkeypatch.setenv("XINV_FUSED_RC", "0")
+    _check(c, "extend", "periodic", 7, rc=False)
+
+
+@pytest.mark.parametrize("variant", ["0", "2", "4"])
 @pytest.mark.parametrize("rb", ["1", "3", "8", "17"])
 @pytest.mark.parametrize("bcy,bcx", BCS)
 def test_fused_many_strips(gpu_ctx, monkeypatch, variant, rb, bcy, bcx):
     """Force tiny strips: every strip boundary (rows and columns) falls inside the grid."""
     monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
+    monkeypatch.setenv("XINV_FUSED_RC_VARIANT", variant)
     monkeypatch.setenv("XINV_FUSED_RB", rb)
     for shape in [(41, 130), (64, 256)]:
         c = cases.random_std2d(*shape, with_B=False, seed=shape[0] + 7 * shape[1])
+        r = cases.random_std2d_rowcoef(*shape, seed=shape[0] + 7 * shape[1] + 1)
         for sweeps in (0, 4, 5):
-            _check(c, bcy, bcx, sweeps)
+            _check(c, bcy, bcx, sweeps, rc=False)
+            _check(r, bcy, bcx, sweeps, rc=True)
 
 
+@pytest.mark.parametrize("rcflag", ["0", "1"])
 @pytest.mark.parametrize("variant", VARIANTS)
-def test_fused_poisson_to_tolerance(gpu_ctx, monkeypatch, variant):
+def test_fused_poisson_to_tolerance(gpu_ctx, monkeypatch, variant, rcflag):
     monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
+    monkeypatch.setenv("XINV_FUSED_RC_VARIANT", variant)
+    monkeypatch.setenv("XINV_FUSED_RC", rcflag)
     c = cases.poisson_latlon(90, 180, land=True, noise=1e-6, seed=0)
-    _check(c, "extend", "periodic", 5000, tol=1e-8)
-    _check(c, "fixed", "periodic", 5000, tol=1e-8)
+    _check(c, "extend", "periodic", 5000, tol=1e-8, rc=(rcflag == "1"))
+    _check(c, "fixed", "periodic", 5000, tol=1e-8, rc=(rcflag == "1"))
 
 
-@pytest.mark.parametrize("variant", ["2", "3", "5"])
-def test_fused_t2_redo_when_stopping_mid_pass(gpu_ctx, monkeypatch, variant):
+@pytest.mark.parametrize("rcflag", ["0", "1"])
+@pytest.mark.parametrize("variant", ["1", "2", "3"])
+def test_fused_t2_redo_when_stopping_mid_pass(gpu_ctx, monkeypatch, variant, rcflag):
     """T = 2: tolerances chosen so that the stop test fires after the 1st and after the
     2nd iteration of a pass (even and odd sweep counts); the overshoot is rolled back."""
     monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
+    monkeypatch.setenv("XINV_FUSED_RC_VARIANT", variant)
+    monkeypatch.setenv("XINV_FUSED_RC", rcflag)
     c = cases.poisson_latlon(60, 120, land=True, noise=1e-6, seed=5)
     seen = set()
     for tol in (3e-3, 2e-3, 1e-3, 7e-4, 5e-4, 3e-4, 2e-4, 1e-4, 5e-5):
@@ -96,10 +132,12 @@ def test_fused_odd_nx_periodic_falls_back_to_colour_engine(gpu_ctx):
     assert xb.default_context().stats()["engine"] == "colour"
 
 
+@pytest.mark.parametrize("rcflag", ["0", "1"])
 @pytest.mark.parametrize("shared", [True, False])
-def test_fused_batched_freeze(gpu_ctx, shared):
+def test_fused_batched_freeze(gpu_ctx, monkeypatch, shared, rcflag):
     """Batch of slices with shared (stride 0) or per-slice coefficients; every slice
     stops on its own test and equals its single-slice oracle run."""
+    monkeypatch.setenv("XINV_FUSED_RC", rcflag)
     B = 4
     c = cases.poisson_latlon(60, 124, land=True, noise=1e-6, seed=2, batch=B)
     for b in range(B):

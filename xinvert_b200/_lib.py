@@ -35,7 +35,7 @@ class XinvStats(C.Structure):
                 ("engine", C.c_int32), ("ncolours", C.c_int32),
                 ("sweep_ms", C.c_double), ("dom_ms", C.c_double),
                 ("dom_launches", C.c_int64), ("slow_strips", C.c_int64),
-                ("iters_per_pass", C.c_int32), ("pad_", C.c_int32)]
+                ("iters_per_pass", C.c_int32), ("row_coeffs", C.c_int32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

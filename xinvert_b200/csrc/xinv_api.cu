@@ -90,7 +90,7 @@ struct xinv_ctx {
     size_t prof_used = 0;
     // workspace (grown on demand, reused across calls)
     DevBuf stage[10];            // staged S, S2 and up to 8 coefficient arrays
-    DevBuf state, psum, pcnt, ticket, nactive;
+    DevBuf state, psum, pcnt, ticket, nactive, flags_in;
     XmWork xm_work;              // padded operand copies of the fused engine
     int *h_nactive_pinned = nullptr;
     Problem pb;
@@ -177,7 +177,7 @@ extern "C" void xinv_destroy(xinv_ctx *c)
     cudaStreamSynchronize(c->stream);
     xinv_nccl_finalize(c);
     for (auto &b : c->stage) release(b);
-    release(c->state); release(c->psum); release(c->pcnt); release(c->ticket); release(c->nactive);
+    release(c->state); release(c->psum); release(c->pcnt); release(c->ticket); release(c->nactive); release(c->flags_in);
     release(c->nccl_buf);
     fused_plan_release(c->pb.fused);
     xm_work_release(c->xm_work);
@@ -444,8 +444,8 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     if ((rc = ensure(c->state, sizeof(XdSliceState) * a.batch))) return rc;
     if ((rc = ensure(c->nactive, 64))) return rc;
     if ((rc = ensure(c->ticket, sizeof(unsigned) * a.batch))) return rc;
-    // flags in -> device (reuse psum buffer temporarily is awkward; use a small staging alloc)
-    DevBuf ftmp;
+    // flags in -> device
+    DevBuf &ftmp = c->flags_in;
     if ((rc = ensure(ftmp, sizeof(double) * 3 * a.batch))) return rc;
     CK(cudaMemcpyAsync(ftmp.p, a.flags, sizeof(double) * 3 * a.batch, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->ticket.p, 0, sizeof(unsigned) * a.batch, c->stream));
@@ -455,12 +455,12 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
             (XdSliceState *)c->state.p, (const double *)ftmp.p, (int)a.batch, (int *)c->nactive.p, nit0);
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));
-    release(ftmp);
+    CK(cudaStreamSynchronize(c->stream));       // a.flags (caller's host memory) has been read
     pb.h_nactive = (int)a.batch;
 
     c->stats.engine = pb.engine;
     c->stats.iters_per_pass = (pb.engine == XINV_ENGINE_FUSED) ? pb.fused.T : 1;
+    c->stats.row_coeffs = (pb.engine == XINV_ENGINE_FUSED && pb.fused.rc) ? 1 : 0;
     pb.open = true;
     return XINV_OK;
 }
@@ -540,11 +540,14 @@ static int sweep_colour_engine(xinv_ctx *c, Problem &pb)
 static int auto_check_every(const xinv_ctx *c, const Problem &pb)
 {
     if (pb.check_every > 0) return pb.check_every;
-    // aim at ~300 us of device work between host polls; a sweep moves ~80 B/cell
-    const double est_us = 4.0 + (double)pb.g.N * (double)pb.batch * 80.0 / 4.0e6;  // 4 TB/s = 4e6 B/us
-    int k = (int)(300.0 / est_us);
-    if (k < 4) k = 4;
-    if (k > 64) k = 64;
+    // Aim at ~2 ms of device work between host polls of the active count.  Passes launched
+    // after every slice has stopped find nothing to do (a few microseconds each), so polling
+    // rarely costs little; polling often costs a stream synchronisation per poll.
+    const double bytes_per_pass = (double)pb.g.N * (double)pb.batch * (pb.engine == XINV_ENGINE_FUSED ? 40.0 : 80.0);
+    const double est_us = 5.0 + bytes_per_pass / 4.0e6;             // ~4 TB/s = 4e6 B/us
+    int k = (int)(2000.0 / est_us);
+    if (k < 8) k = 8;
+    if (k > 256) k = 256;
     (void)c;
     return k;
 }
@@ -569,27 +572,32 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
             rc = lex_sweep(c->stream, pb.kind, pb.hasB, pb.g, pb.q, pb.batch, pb.dS, (XdSliceState *)c->state.p,
                            pb.nblk_norm, (double *)c->psum.p, (i64 *)c->pcnt.p, (unsigned *)c->ticket.p,
                            (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
-        else if (pb.engine == XINV_ENGINE_FUSED) {
-            prof_mark(c, pb);
+        else if (pb.engine == XINV_ENGINE_FUSED)
             rc = fused_sweep(pb.fused, c->stream, (XdSliceState *)c->state.p, (double *)c->psum.p, (i64 *)c->pcnt.p,
                              (unsigned *)c->ticket.p, (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
-            prof_mark(c, pb);
-        } else
+        else
             rc = sweep_colour_engine(c, pb);
         if (rc) return rc;
     }
     pb.sweeps_launched += sweeps;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));     // [ev0, ev1] = the kernels of this chunk, back to back
     CK(cudaMemcpyAsync(c->h_nactive_pinned, c->nactive.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->stats.solve_ms += ms;
-    if (pb.profile) prof_collect(c, pb.engine == XINV_ENGINE_FUSED ? 1 : pb.g.ncol);
+    if (pb.profile) {
+        if (pb.engine == XINV_ENGINE_FUSED && pb.ordering != XINV_ORDER_LEX) {
+            // the chunk holds nothing but fused passes: its event bracket is their summed duration
+            // (inter-launch gaps included), without an event pair around every launch
+            c->stats.dom_ms += ms;
+            c->stats.dom_launches += sweeps;
+        } else
+            prof_collect(c, pb.g.ncol);
+    }
     c->stats.sweeps_launched = pb.sweeps_launched;
     pb.h_nactive = c->h_nactive_pinned[0];
-    c->stats.slow_strips = c->h_nactive_pinned[1];
     if (pb.h_nactive != 0 && pb.sweeps_launched >= max_passes)
         return set_err(XINV_E_STATE, "internal error: %d slices still active after %lld passes", pb.h_nactive,
                        (long long)max_passes);
