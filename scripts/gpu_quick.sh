@@ -24,3 +24,9 @@ if [ -n "$NCU" ]; then
   XINV_FUSED_RC_VARIANT=$NCU ncu --set full --clock-control none --import-source on -k regex:xm_std2d -s 4 -c 1 -o $OUT/fused_full \
     python bench.py --steps 1 --warmup 1 --sweeps 20 --cpu-sweeps 2 > $OUT/ncu_full.log 2>&1
 fi
+if [ -n "$CONFIGS" ]; then python scripts/bench_configs.py > $OUT/configs.jsonl 2> $OUT/configs.err; python - $OUT/configs.jsonl <<'PY'
+import json, sys
+for l in open(sys.argv[1]):
+    d = json.loads(l); print("%-42s %.3e cell-updates/s  %.2f us/sweep  api %.3e" % (d["config"], d["gpu_cell_updates_per_s"], d["us_per_sweep"], d["api_cell_updates_per_s"]))
+PY
+fi
