@@ -212,9 +212,9 @@ def run_ours(args):
         torch.cuda.synchronize()          # torch stream -> library stream hand-over (a 52 MB memset-like copy)
         return xd.solve_standard_2D_sharded(dS, dA, None, dC, dF, *pos, allreduce=allreduce, profile=profile, **kw)
 
-    def step_host():
-        S = hS
-        S[...] = c["S0"]
+    def step_host(S):
+        # S is in/out: every step gets its own pinned buffer holding the initial guess, prepared
+        # before the timed region, so the region holds the API call (H2D + solve + D2H) and nothing else
         return xd.solve_standard_2D_sharded(S, c["A"], None, c["C"], c["F"], *pos, allreduce=allreduce, **kw)
 
     for _ in range(args.warmup):
@@ -241,15 +241,19 @@ def run_ours(args):
     engine_used, ncol = st["engine"], st["ncolours"]
 
     # ---- end to end through the C-ABI with host buffers ---------------------
-    hS = xb.pinned_empty(c["S0"].shape)
-    step_host()
+    e2e_steps = max(1, min(args.steps, 5))
+    hS = []
+    for _ in range(e2e_steps + 1):
+        buf = xb.pinned_empty(c["S0"].shape)
+        buf[...] = c["S0"]
+        hS.append(buf)
+    step_host(hS[e2e_steps])
     barrier()
     t1 = time.perf_counter()
     ctx.timer_start()
     h2d = d2h = 0
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        _, st_h, _ = step_host()
+    for i in range(e2e_steps):
+        _, st_h, _ = step_host(hS[i])
         h2d, d2h = st_h["h2d_bytes"], st_h["d2h_bytes"]
     ev_e2e = ctx.timer_stop() / 1e3
     barrier()
@@ -293,8 +297,18 @@ def run_ours(args):
         alg_bytes = 32.0 * N * per_gpu          # one colour sweep: S 8N r + 4N w, A 8N, C 8N, F 4N
         kern = "colour sweep kernel (one launch per colour)"
     achieved = (alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9) if dom_n else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel from the committed
+    # `ncu --set full` capture (profiles/traffic.json; C2 workload, one slice per GPU)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = ("fused_rc" if st["row_coeffs"] else "fused_general") if engine_used == "fused" else "colour"
+        if args.workload == "c2":
+            traffic = tj[key]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel": kern, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "avg_launch_us": (dom_ms / dom_n * 1e3) if dom_n else None, "timed_launches": dom_n}
 
@@ -318,7 +332,8 @@ def run_ours(args):
                    "wall_ms_per_step": 1e3 * wall / args.steps},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "ms_per_step": 1e3 * ev_e2e / e2e_steps},
+                "steps": e2e_steps, "ms_per_step": 1e3 * ev_e2e / e2e_steps,
+                "h2d_ms": st_h["h2d_ms"], "d2h_ms": st_h["d2h_ms"]},
         "gpu_launches": int(tot_launch.item()), "clocks": clk,
     }
     print(json.dumps(line), flush=True)

@@ -3,7 +3,7 @@
 #   VARIANTS="0 2" RCVARIANTS="1 2" NCU=rc1 bash scripts/gpu_quick.sh <tag>
 TAG=${1:-quick}; shift
 OUT=gpurun_out/$TAG; mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q ${PYTEST_ARGS} > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest.log
 show() { python - "$1" "$2" <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r = d["roofline"]

@@ -94,6 +94,21 @@ def random_gen2d(ny, nx, with_B, seed, land=0.1, batch=None):
     return dict(A=A, B=B, C=C, D=D, E=E, F=F, G=G, S0=S0, p=p)
 
 
+def random_gen2d_rowcoef(ny, nx, seed, land=0.1, batch=None, undef_rows=False):
+    """random_gen2d (B == 0) with A, C, D, E, F varying with y only -- the structure of the
+    Gill-Matsuno and Stommel problems -- which the fused engine handles."""
+    c = random_gen2d(ny, nx, False, seed, land=land, batch=batch)
+    rng = np.random.default_rng(seed + 54321)
+    vals = dict(A=-(1.0 + 0.3 * rng.random(ny)), C=-(1.0 + 0.3 * rng.random(ny)), D=1e-6 * rng.standard_normal(ny),
+                E=1e-6 * rng.standard_normal(ny), F=1e-12 * rng.random(ny))
+    if undef_rows and ny > 8:
+        vals["D"][ny // 3] = UNDEF
+        vals["A"][ny // 2] = UNDEF
+    for k, v in vals.items():
+        c[k] = np.ascontiguousarray(np.broadcast_to(v[:, None], (ny, nx)))
+    return c
+
+
 def random_std3d(nz, ny, nx, seed, land=0.1, batch=None):
     rng = np.random.default_rng(seed)
     shape = (nz, ny, nx) if batch is None else (batch, nz, ny, nx)

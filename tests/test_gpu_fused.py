@@ -31,7 +31,7 @@ def _check(c, bcy, bcx, sweeps, tol=-1.0, omega=1.4, rc=None):
         assert st["row_coeffs"] == int(rc)
     assert np.array_equal(S_g, S_o), f"max diff {np.abs(S_g - S_o).max()} at {np.argwhere(S_g != S_o)[:5]}"
     assert f_g[0] == f_o[0] and f_g[2] == f_o[2]
-    assert np.isclose(f_g[1], f_o[1], rtol=1e-6, atol=1e-18)
+    assert np.isclose(f_g[1], f_o[1], rtol=1e-6, atol=1e-13)    # a difference of two norms: tree sum (GPU) vs serial sum (oracle)
 
 
 VARIANTS = ["0", "1", "2", "3", "4"]          # both tables have five entries

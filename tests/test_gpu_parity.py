@@ -26,7 +26,7 @@ BCS = [("fixed", "fixed"), ("fixed", "periodic"), ("extend", "fixed"), ("extend"
 def _check_flags(f_gpu, f_ref):
     assert f_gpu[0] == f_ref[0]
     assert f_gpu[2] == f_ref[2]
-    assert np.isclose(f_gpu[1], f_ref[1], rtol=1e-6, atol=1e-18)
+    assert np.isclose(f_gpu[1], f_ref[1], rtol=1e-6, atol=1e-13)
 
 
 @pytest.mark.parametrize("bcy,bcx", BCS)
