@@ -123,45 +123,88 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-def cpu_reference_rate(name, sweeps, rank=0):
-    """Reference algorithm (lexicographic SOR, numbas.py:215-416) through the C
-    oracle port on ONE host thread -- the reference is single-threaded by
-    construction (SURVEY.md fact 1) and one slice cannot use more."""
-    import oracle
-    from tests import cases
+def cpu_case(name, rank=0):
+    """One slice of this rank's shard as the C oracle wants it (2-D arrays)."""
     c, bcs = make_problem(name, rank)
-    p = c["p"]
     S0 = c["S0"] if c["S0"].ndim == 2 else c["S0"][0]
     F = c["F"] if c["F"].ndim == 2 else c["F"][0]
-    cc = dict(A=c["A"], C=c["C"], F=F, S0=S0, p=p)
-    cases.run_std2d(oracle, dict(cc, S0=S0.copy()), bcs[0], bcs[1], 0, -1.0)       # warm caches / page in
+    return dict(A=c["A"], C=c["C"], F=F, S0=S0, p=c["p"]), bcs
+
+
+def cpu_solve(case, bcs, sweeps):
+    """`sweeps` lexicographic SOR sweeps (numbas.py:215-416) through the C oracle port on the
+    calling thread; returns the seconds spent in the solve."""
+    import oracle
+    from tests import cases
     t0 = time.perf_counter()
-    _, fl = cases.run_std2d(oracle, cc, bcs[0], bcs[1], sweeps - 1, -1.0)
+    _, fl = cases.run_std2d(oracle, case, bcs[0], bcs[1], sweeps - 1, -1.0)
     dt = time.perf_counter() - t0
     assert int(fl[2]) + 1 == sweeps
-    return sweeps * S0.size / dt, dt
+    return dt
+
+
+def cpu_reference_rate(name, sweeps, rank=0):
+    """Reference algorithm on ONE host thread -- the reference is single-threaded by
+    construction (SURVEY.md fact 1) and one slice cannot use more."""
+    case, bcs = cpu_case(name, rank)
+    cpu_solve(case, bcs, 1)                                          # warm caches / page in
+    dt = cpu_solve(case, bcs, sweeps)
+    return sweeps * case["S0"].size / dt, dt
+
+
+_REF_JOB = None
+
+
+def _ref_worker_init(workload, world):
+    global _REF_JOB
+    ident = mp_ident()
+    _REF_JOB = cpu_case(workload, ident % world)
+    cpu_solve(_REF_JOB[0], _REF_JOB[1], 1)
+
+
+def mp_ident():
+    import multiprocessing as mp
+    idt = mp.current_process()._identity
+    return (idt[0] - 1) if idt else 0
+
+
+def _ref_worker_solve(nsw):
+    return cpu_solve(_REF_JOB[0], _REF_JOB[1], nsw)
 
 
 def run_reference(args):
+    """The reference's own algorithm on the host cores: every slice is an independent,
+    inherently serial solve (lexicographic Gauss-Seidel), so the job -- one slice per GPU for
+    c2/c1, 32 per GPU for c5 -- can use one host thread per slice and no more."""
     rank, _, world = env_rank()
     if rank != 0:
         return
+    import multiprocessing as mp
     ny, nx, per_gpu, bcs, desc = WORKLOADS[args.workload]
-    sweeps = args.ref_sweeps or max(2, int(round(2.0e8 / (ny * nx))))          # ~2-3 s of CPU per step
+    nslices = world * per_gpu
+    nthreads = max(1, min(nslices, os.cpu_count() or 1))
+    sweeps = args.ref_sweeps or max(2, int(round(2.0e8 / (ny * nx))))          # ~2-3 s of CPU per step and thread
+    # one worker process per slice (each builds its own slice once, then only solves)
+    pool = mp.get_context("fork").Pool(nthreads, initializer=_ref_worker_init, initargs=(args.workload, max(1, world)))
+
+    def step(nsw):
+        t0 = time.perf_counter()
+        pool.map(_ref_worker_solve, [nsw] * nthreads, chunksize=1)
+        return time.perf_counter() - t0
+
     for _ in range(args.warmup):
-        cpu_reference_rate(args.workload, max(2, sweeps // 8))
-    rates, times = [], []
-    for _ in range(args.steps):
-        r, dt = cpu_reference_rate(args.workload, sweeps)
-        rates.append(r); times.append(dt)
-    value = sweeps * ny * nx * args.steps / sum(times)
-    sample = f"{sweeps} lexicographic sweeps of one {nx}x{ny} slice per step, C port of numbas.py (gcc -O2, no FMA)"
+        step(max(2, sweeps // 8))
+    times = [step(sweeps) for _ in range(args.steps)]
+    value = nthreads * sweeps * ny * nx * args.steps / sum(times)
+    pool.close()
+    sample = (f"{sweeps} lexicographic sweeps of {nthreads} {nx}x{ny} slice(s) per step, one host process per slice "
+              f"({nthreads} of {os.cpu_count()} cores; the job has {nslices} slices), C port of numbas.py (gcc -O2, no FMA)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
