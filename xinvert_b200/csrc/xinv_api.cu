@@ -566,18 +566,22 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
     if (sweeps <= 0) sweeps = auto_check_every(c, pb);
     if (sweeps > remaining) sweeps = remaining;
     CK(cudaEventRecord(c->ev0, c->stream));
-    for (i64 it = 0; it < sweeps; ++it) {
+    for (i64 it = 0; it < sweeps;) {
         int rc;
+        i64 did = 1;
         if (pb.ordering == XINV_ORDER_LEX)
             rc = lex_sweep(c->stream, pb.kind, pb.hasB, pb.g, pb.q, pb.batch, pb.dS, (XdSliceState *)c->state.p,
                            pb.nblk_norm, (double *)c->psum.p, (i64 *)c->pcnt.p, (unsigned *)c->ticket.p,
                            (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
-        else if (pb.engine == XINV_ENGINE_FUSED)
+        else if (pb.engine == XINV_ENGINE_FUSED) {
+            did = sweeps - it < pb.fused.ppl ? sweeps - it : pb.fused.ppl;       // passes in this launch
             rc = fused_sweep(pb.fused, c->stream, (XdSliceState *)c->state.p, (double *)c->psum.p, (i64 *)c->pcnt.p,
-                             (unsigned *)c->ticket.p, (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
-        else
+                             (unsigned *)c->ticket.p, (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, (int)did,
+                             &c->stats.kernel_launches);
+        } else
             rc = sweep_colour_engine(c, pb);
         if (rc) return rc;
+        it += did;
     }
     pb.sweeps_launched += sweeps;
     CK(cudaGetLastError());
