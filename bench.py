@@ -71,8 +71,10 @@ def make_problem(name, rank, pinned=False):
 
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  The sampler is started before the
+    warm-up steps (nvidia-smi needs a few hundred ms to produce its first line) and the samples are
+    filtered afterwards to the wall-clock window of the timed region."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -84,12 +86,14 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=self.f,
+                                          "-i", str(self.idx), "-lms", "50"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (datetime start, datetime end) of the timed region (local time)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -99,26 +103,36 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in open(self.path):
                 p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
+                if len(p) < 10:
                     continue
                 try:
-                    sm.append(float(p[1])); mx.append(float(p[2]))
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f")
+                    rows.append((ts, float(p[2]), float(p[3]), float(p[4]),
+                                 [n for n, v in zip(names, p[6:10]) if v.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for nme, v in zip(names, p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
-        out["reasons"] = sorted(reasons)
+        sel, note = rows, "all samples (warm-up + timed region + e2e)"
+        if window is not None:
+            inside = [r for r in rows if window[0] <= r[0] <= window[1]]
+            if len(inside) >= 2:
+                sel, note = inside, "samples inside the timed region"
+            else:                                    # a very short region: take the samples under load around it
+                pad = datetime.timedelta(milliseconds=300)
+                near = [r for r in rows if window[0] - pad <= r[0] <= window[1] + pad]
+                if near:
+                    sel, note = near, "timed region shorter than the sampling period: samples within 300 ms of it"
+        if sel:
+            out.update(sm_mhz=float(np.median([r[1] for r in sel])), sm_max_mhz=float(max(r[2] for r in sel)),
+                       samples=len(sel), power_w_max=float(max(r[3] for r in sel)), note=note)
+            out["reasons"] = sorted({n for r in sel for n in r[4]})
         return out
 
 
@@ -260,16 +274,18 @@ def run_ours(args):
         # before the timed region, so the region holds the API call (H2D + solve + D2H) and nothing else
         return xd.solve_standard_2D_sharded(S, c["A"], None, c["C"], c["F"], *pos, allreduce=allreduce, **kw)
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
+    import datetime
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
     launches = 0
     solve_ms = 0.0
     dom_ms, dom_n = 0.0, 0
     t0 = time.perf_counter()
+    w0 = datetime.datetime.now()
     ctx.timer_start()                          # CUDA events on the library's stream bracket the K steps
     for _ in range(args.steps):
         fl, st, _ = step_device(profile=True)
@@ -277,9 +293,9 @@ def run_ours(args):
         solve_ms += st["solve_ms"]
         dom_ms += st["dom_ms"]; dom_n += st["dom_launches"]
     ev_s = ctx.timer_stop() / 1e3
+    w1 = datetime.datetime.now()
     barrier()
     wall = time.perf_counter() - t0
-    clk = clocks.stop() if rank == 0 else None
     assert int(fl[0, 2]) + 1 == sweeps, (fl[0], sweeps)
     engine_used, ncol = st["engine"], st["ncolours"]
 
@@ -301,6 +317,7 @@ def run_ours(args):
     ev_e2e = ctx.timer_stop() / 1e3
     barrier()
     wall_e2e = time.perf_counter() - t1
+    clk = clocks.stop((w0, w1)) if rank == 0 else None
 
     # ---- reduce over ranks: device time of the timed region = max over ranks ----
     t_dev = solve_ms / 1e3
