@@ -578,6 +578,7 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
             rc = fused_sweep(pb.fused, c->stream, (XdSliceState *)c->state.p, (double *)c->psum.p, (i64 *)c->pcnt.p,
                              (unsigned *)c->ticket.p, (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, (int)did,
                              &c->stats.kernel_launches);
+            if (rc) return set_err(XINV_E_CUDA, "fused engine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else
             rc = sweep_colour_engine(c, pb);
         if (rc) return rc;
