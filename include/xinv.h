@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define XINV_VERSION 100
+#define XINV_VERSION 101
 
 /* boundary conditions (numbas.py BCy/BCx strings 'fixed' / 'extend' / 'periodic') */
 #define XINV_BC_FIXED    0
@@ -133,6 +133,28 @@ int xinv_std2d(xinv_ctx *ctx, double *S, const double *A, const double *B,
                double delxSqr, double ratioQtr, double ratioSqr,
                double optArg, double undef, double *flags,
                int64_t mxLoop, double tolerance, const xinv_opts *opts);
+
+/* Poisson-type front end: the host-side preparation of apps.__mask_FS,
+ * apps.__coeffs_Poisson and the de-masking of apps.__template (apps.py:2112-2159, :1397-1437,
+ * :1386-1392) done on the device, for the common case icbc == None:
+ *   F_user      the user's forcing [batch][ny][nx]; cells equal to user_undef (any NaN when
+ *               user_undef is NaN) are masked ("land");
+ *   F_row_scale [ny] or NULL: the forcing of row j is multiplied by F_row_scale[j]
+ *               (lat-lon: cos(lat), apps.py:1409) -- one IEEE multiply, as the reference does;
+ *   A_rows, C_rows  [ny]: coefficients constant along x (apps.py:1405-1408: cosH, 1/cosG;
+ *               cartesian: 1), shared by the whole batch;
+ *   S_out       [batch][ny][nx], output only: the solve starts from 0 (initS, apps.py:2145) and
+ *               masked cells are set to out_undef on return (apps.py:1389-1392).
+ * Numerically identical to building full arrays on the host and calling xinv_std2d.  Needs the
+ * fused engine (2-D, even nx when periodic-x): otherwise XINV_E_UNSUPPORTED and the caller falls
+ * back to xinv_std2d; also when an unmasked forcing value is not finite (the reference's
+ * `maskF - maskF` template is not zero then and the host path reproduces its quirks). */
+int xinv_std2d_rows(xinv_ctx *ctx, double *S_out, const double *A_rows, const double *C_rows,
+                    const double *F_user, const double *F_row_scale, double user_undef, double out_undef,
+                    int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                    double delxSqr, double ratioQtr, double ratioSqr,
+                    double optArg, double undef, double *flags,
+                    int64_t mxLoop, double tolerance, const xinv_opts *opts);
 
 /* Replaces core.inv_general2D -> numbas.invert_general_2D
  * (core.py:418-428, numbas.py:987-1201).  B == NULL means B == 0. */

@@ -50,6 +50,20 @@ def poisson_latlon(ny, nx, land=True, noise=1e-6, seed=0, batch=None, phase=0.0)
     return dict(A=A, C=C, F=F, p=p, S0=np.zeros(shape))
 
 
+def poisson_latlon_user(ny, nx, land=True, noise=1e-6, seed=0, phase=0.0):
+    """The same problem as poisson_latlon the way a user of invert_Poisson holds it: the raw
+    vorticity (NaN on land) and the lat / lon coordinates."""
+    dlat, dlon = 180.0 / ny, 360.0 / nx
+    lat = -90.0 + dlat / 2 + dlat * np.arange(ny)
+    lon = dlon * np.arange(nx)
+    lam, phi = np.deg2rad(lon)[None, :], np.deg2rad(lat)[:, None]
+    rng = np.random.default_rng(seed)
+    zeta = 1e-5 * np.sin(3 * lam + phase) * np.cos(phi) ** 2 * np.sin(2 * phi) + noise * rng.standard_normal((ny, nx))
+    if land:
+        zeta[np.sin(5 * lam) * np.cos(3 * phi) > 0.6] = np.nan
+    return zeta, lat, lon
+
+
 def random_std2d(ny, nx, with_B, seed, land=0.1, batch=None):
     rng = np.random.default_rng(seed)
     shape = (ny, nx) if batch is None else (batch, ny, nx)

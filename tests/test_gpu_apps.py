@@ -221,3 +221,55 @@ def test_stommel_idealized_fused_general_form(gpu_ctx, capsys):
         S_o = _via_oracle(xb.invert_Stommel, curl, iParams=dict(base, printInfo=False), **kw)
         assert np.array_equal(S_g.values, S_o.values)
         assert np.isclose(S_g.max(), mx, rtol=1e-6)          # same fixed point as the reference ordering
+
+
+@pytest.mark.parametrize("coords,bcs", [("lat-lon", ["extend", "periodic"]), ("lat-lon", ["fixed", "periodic"]),
+                                        ("cartesian", ["fixed", "fixed"])])
+def test_poisson_device_front_end_equals_host_path(gpu_ctx, monkeypatch, coords, bcs):
+    """invert_Poisson with icbc=None goes through xinv_std2d_rows (masking, coefficients, forcing
+    scale and de-masking on the device); forcing it onto the reference-shaped host path must give the
+    same bits, the same printed loop counts and the same undef pattern -- NaN-marked and
+    value-marked land, batched over a time axis."""
+    from xinvert_b200 import apps
+    ny, nx, T = 90, 180, 3
+    zeta, co = _c1_zeta(ny, nx)
+    rng = np.random.default_rng(2)
+    z = np.stack([zeta * (1 + 0.5 * t) + 1e-6 * rng.standard_normal((ny, nx)) for t in range(T)])
+    lam, phi = np.deg2rad(co['lon'])[None, :], np.deg2rad(co['lat'])[:, None]
+    land = np.sin(5 * lam) * np.cos(3 * phi) > 0.6
+    if coords == "cartesian":
+        co = {'lat': 1e5 * np.arange(ny), 'lon': 1e5 * np.arange(nx)}
+    for undef in (np.nan, -9999.0):
+        zz = z.copy()
+        zz[:, land] = undef
+        F = DA(zz, ['time', 'lat', 'lon'], dict(co, time=np.arange(T)))
+        ip = {'BCs': bcs, 'tolerance': 1e-9, 'mxLoop': 3000, 'undef': undef, 'printInfo': False}
+        calls = []
+        real = apps._device_solvers.solve_standard_2D_rows
+        monkeypatch.setattr(apps._device_solvers, "solve_standard_2D_rows", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+        s_f = xb.invert_Poisson(F, dims=['lat', 'lon'], coords=coords, iParams=dict(ip))
+        assert calls, "the device front end was not used"
+        monkeypatch.setattr(apps, "_poisson_device_front", lambda *a, **k: None)
+        s_h = xb.invert_Poisson(F, dims=['lat', 'lon'], coords=coords, iParams=dict(ip))
+        monkeypatch.undo()
+        assert np.array_equal(s_f.values, s_h.values, equal_nan=True)
+        lv = s_f.values[:, land]
+        assert np.isnan(lv).all() if np.isnan(undef) else (lv == undef).all()
+        assert np.isfinite(s_f.values[:, ~land]).all() and np.abs(s_f.values[:, ~land]).max() > 0
+
+
+def test_poisson_device_front_end_falls_back(gpu_ctx):
+    """Inputs the front end does not take (odd nx with periodic-x; an infinite forcing value) still
+    give the host path's answer."""
+    zeta, co = _c1_zeta(30, 61)
+    F = DA(zeta, ['lat', 'lon'], co)
+    ip = {'BCs': ['fixed', 'periodic'], 'tolerance': 1e-9, 'mxLoop': 200, 'printInfo': False}
+    s = xb.invert_Poisson(F, dims=['lat', 'lon'], iParams=dict(ip))
+    s_o = _via_oracle(xb.invert_Poisson, F, dims=['lat', 'lon'], iParams=dict(ip))
+    assert np.array_equal(s.values, s_o.values)
+    zeta, co = _c1_zeta(30, 60)
+    zeta[7, 9] = np.inf
+    F = DA(zeta, ['lat', 'lon'], co)
+    s = xb.invert_Poisson(F, dims=['lat', 'lon'], iParams=dict(ip))
+    s_o = _via_oracle(xb.invert_Poisson, F, dims=['lat', 'lon'], iParams=dict(ip))
+    assert np.array_equal(s.values, s_o.values, equal_nan=True)

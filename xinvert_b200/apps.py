@@ -29,6 +29,8 @@ import copy
 import numpy as np
 
 from . import core
+from . import solvers as _device_solvers
+from ._lib import XinvError
 from .xrshim import coord_values, wrap_like
 
 _undeftmp = -9.99e8
@@ -70,7 +72,14 @@ default_mParams = copy.deepcopy({
 # ---------------------------------------------------------------------------
 def invert_Poisson(F, dims, coords='lat-lon', icbc=None,
                    mParams=default_mParams, iParams=default_iParams):
-    r"""Invert :math:`\psi_{yy} + \psi_{xx} = F` for :math:`\psi` (apps.py:67-100)."""
+    r"""Invert :math:`\psi_{yy} + \psi_{xx} = F` for :math:`\psi` (apps.py:67-100).
+
+    With ``icbc=None`` (the common case) the masking, the coefficient arrays and the de-masking are
+    done on the device (``xinv_std2d_rows``) from the forcing and three per-row vectors -- same
+    numbers, no full-size host temporaries; anything else takes the reference-shaped host path."""
+    fast = _poisson_device_front(F, dims, coords, icbc, mParams, iParams)
+    if fast is not None:
+        return fast
     return _template(_coeffs_Poisson, core.inv_standard2D, 2, F, dims, coords,
                      icbc, ['g', 'Omega', 'Rearth'], mParams, iParams)
 
@@ -351,6 +360,54 @@ def _coeffs_Poisson(g, coords, mParams, iParams, icbc):
     if B is None:
         B = _Field(zero, g.all_dims) if not z0 else _Field(np.zeros(g.core_shape), g.dims)
     return maskF, Fm, initS, (A, B, C)
+
+
+def _poisson_device_front(F, dims, coords, icbc, mParams, iParams):
+    """invert_Poisson through the device-side front end, or None when the reference-shaped host
+    path has to be taken (icbc given, core dims not trailing, non-float64 input, lexicographic
+    ordering / colour engine requested, odd nx with periodic-x, non-finite forcing values ...).
+    Follows apps.__template (apps.py:1324-1394) step for step; the arrays it would build are
+    described to the library by three vectors along the first core dim instead."""
+    if icbc is not None or len(dims) != 2:
+        return None
+    ip = _update(default_iParams, iParams)
+    if ip.get('ordering', 'colour') not in ('colour', 'color', 'redblack', 'red-black') or \
+            ip.get('engine', 'auto') == 'colour' or core.solvers is not _device_solvers:
+        return None
+    mp = _update(default_mParams, mParams, ['g', 'Omega', 'Rearth'])
+    g = _Grid(F, dims)
+    if not g.trailing or g.values.dtype != np.float64:
+        return None
+    c = coords.lower()
+    ny = g.core_shape[0]
+    if c == 'lat-lon':
+        lats = np.deg2rad(g.coord(0))
+        cosG = np.cos(lats)
+        A_rows, C_rows, scale = np.cos((lats + _shift1(lats)) / 2.0), 1.0 / cosG, cosG
+    elif c == 'z-lat':
+        return None                              # the forcing scale runs along the second core dim
+    elif c in ('z-lon', 'cartesian'):
+        A_rows, C_rows, scale = np.ones(ny), np.ones(ny), None
+    else:
+        return None                              # let the host path raise the reference's exception
+    ps = _cal_params2D(g, coords, mp['Rearth'])
+    ip = _update(ps, ip)
+    if ip['debug']:
+        _print_params(ip)
+    try:
+        S, flags, _ = _device_solvers.solve_standard_2D_rows(
+            g.values, A_rows, C_rows, scale, ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1], ip['del1Sqr'],
+            ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp, ip['flags'], ip['mxLoop'], ip['tolerance'],
+            ctx=ip.get('ctx'))
+    except XinvError as e:
+        if 'error -5' in str(e):                 # XINV_E_UNSUPPORTED: not a problem for the fused engine
+            return None
+        raise
+    _, noncore, _ = core._layout(F, dims)
+    core._report(ip, core._slice_labels(F, noncore), flags)
+    if isinstance(iParams, dict):
+        iParams['flags_all'] = flags
+    return wrap_like(F, S, name='inverted')
 
 
 def _user_field(g, zero, X, name):

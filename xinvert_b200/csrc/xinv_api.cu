@@ -77,6 +77,7 @@ struct Problem {
     int nblk_norm = 0;
     int h_nactive = 0;
     FusedPlan fused{};
+    bool front = false;          // xinv_std2d_rows: S is output only, de-masked on the device
 };
 
 struct xinv_ctx {
@@ -307,6 +308,10 @@ struct BeginArgs {
     i64 mxLoop;
     double tol;
     const xinv_opts *opts;
+    // xinv_std2d_rows (front end): coef[0] = A rows [ny], coef[2] = C rows [ny], coef[3] = user forcing
+    bool front = false;
+    const double *f_scale = nullptr;
+    double user_undef = 0.0, out_undef = 0.0;
 };
 
 static int problem_begin(xinv_ctx *c, const BeginArgs &a)
@@ -376,7 +381,45 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     // ---- staging --------------------------------------------------------
     const size_t slice_bytes = (size_t)g.N * sizeof(double);
     cudaEvent_t e0 = c->ev0, e1 = c->ev1;
-    if (pb.mem_space == XINV_MEM_HOST) {
+    XmFront front;
+    pb.front = a.front;
+    if (a.front) {
+        // the front end hands over A rows, C rows, the user's forcing and the row scale; S is output only
+        if (o.ordering != XINV_ORDER_COLOUR || o.engine == XINV_ENGINE_COLOUR)
+            return set_err(XINV_E_UNSUPPORTED, "xinv_std2d_rows needs the fused engine (colour ordering)");
+        std::string why;
+        if (!fused_plan_supported(pb.kind, false, g, why))
+            return set_err(XINV_E_UNSUPPORTED, "xinv_std2d_rows needs the fused engine: %s", why.c_str());
+        front.on = true;
+        front.user_undef = a.user_undef;
+        front.out_undef = a.out_undef;
+        const size_t row_bytes = (size_t)a.ny * sizeof(double);
+        if (pb.mem_space == XINV_MEM_HOST) {
+            CK(cudaEventRecord(e0, c->stream));
+            int rc = ensure(c->stage[0], slice_bytes * a.batch);            // S (device only until xinv_end)
+            if (rc) return rc;
+            if ((rc = ensure(c->stage[2 + 3], slice_bytes * a.batch))) return rc;   // user forcing
+            if ((rc = ensure(c->stage[2 + 0], 3 * row_bytes))) return rc;           // A rows | C rows | scale
+            double *rows = (double *)c->stage[2].p;
+            CK(cudaMemcpyAsync(c->stage[5].p, a.coef[3], slice_bytes * a.batch, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(rows, a.coef[0], row_bytes, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(rows + a.ny, a.coef[2], row_bytes, cudaMemcpyHostToDevice, c->stream));
+            if (a.f_scale) CK(cudaMemcpyAsync(rows + 2 * a.ny, a.f_scale, row_bytes, cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2d_bytes += (i64)(slice_bytes * a.batch + (a.f_scale ? 3 : 2) * row_bytes);
+            CK(cudaEventRecord(e1, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            c->stats.h2d_ms = ms;
+            pb.dS = (double *)c->stage[0].p;
+            front.F = (const double *)c->stage[5].p;
+            front.Arow = rows; front.Crow = rows + a.ny; front.scale = a.f_scale ? rows + 2 * a.ny : nullptr;
+        } else {
+            pb.dS = a.S;
+            front.F = a.coef[3]; front.Arow = a.coef[0]; front.Crow = a.coef[2]; front.scale = a.f_scale;
+        }
+        for (int m = 0; m < 8; ++m) { pb.q.c[m] = nullptr; pb.q.cs[m] = 0; }
+    } else if (pb.mem_space == XINV_MEM_HOST) {
         CK(cudaEventRecord(e0, c->stream));
         int rc = ensure(c->stage[0], slice_bytes * a.batch);
         if (rc) return rc;
@@ -426,9 +469,10 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     if (pb.ordering == XINV_ORDER_COLOUR && o.engine != XINV_ENGINE_COLOUR) {
         std::string why;
         if (fused_plan_supported(pb.kind, pb.hasB, g, why)) {
-            rc = fused_plan_build(pb.fused, c->xm_work, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, pb.mxLoop, c->stream, why);
+            rc = fused_plan_build(pb.fused, c->xm_work, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, pb.mxLoop, c->stream, why,
+                                  a.front ? &front : nullptr);
             if (rc == 0) pb.engine = XINV_ENGINE_FUSED;
-            else if (o.engine == XINV_ENGINE_FUSED)
+            else if (o.engine == XINV_ENGINE_FUSED || a.front)
                 return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
         } else if (o.engine == XINV_ENGINE_FUSED) {
             return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
@@ -456,6 +500,14 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));       // a.flags (caller's host memory) has been read
+    if (a.front) {                              // did the front end meet a non-finite unmasked forcing value?
+        int fl[2] = {0, 0};
+        CK(cudaMemcpy(fl, c->xm_work.p[7], sizeof fl, cudaMemcpyDeviceToHost));
+        if (fl[1]) {
+            fused_plan_release(pb.fused);
+            return set_err(XINV_E_UNSUPPORTED, "xinv_std2d_rows: an unmasked forcing value is not finite (use xinv_std2d)");
+        }
+    }
     pb.h_nactive = (int)a.batch;
 
     c->stats.engine = pb.engine;
@@ -680,6 +732,25 @@ extern "C" int xinv_std2d_begin(xinv_ctx *ctx, double *S, const double *A, const
     a.p[0] = delxSqr; a.p[1] = ratioQtr; a.p[2] = ratioSqr;
     a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
     return problem_begin(ctx, a);
+}
+
+extern "C" int xinv_std2d_rows(xinv_ctx *ctx, double *S_out, const double *A_rows, const double *C_rows,
+                               const double *F_user, const double *F_row_scale, double user_undef, double out_undef,
+                               int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                               double delxSqr, double ratioQtr, double ratioSqr,
+                               double optArg, double undef, double *flags,
+                               int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    BeginArgs a{};
+    a.kind = XD_STD2D; a.S = S_out;
+    a.coef[0] = A_rows; a.coef[1] = nullptr; a.coef[2] = C_rows; a.coef[3] = F_user; a.ncoef = 4; a.b_index = 1;
+    a.batch = batch; a.nz = 1; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delxSqr; a.p[1] = ratioQtr; a.p[2] = ratioSqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    a.front = true; a.f_scale = F_row_scale; a.user_undef = user_undef; a.out_undef = out_undef;
+    int rc = problem_begin(ctx, a);
+    if (rc) return rc;
+    return run_to_completion(ctx);
 }
 
 extern "C" int xinv_gen2d_begin(xinv_ctx *ctx, double *S, const double *A, const double *B,

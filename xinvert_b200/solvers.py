@@ -150,6 +150,59 @@ def solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, opt
     return _run("std2d", ops, tail, flags, ordering, engine, check_every, ctx, profile)
 
 
+def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_undef, BCy, BCx,
+                           delxSqr, ratioQtr, ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0),
+                           mxLoop=5000, tolerance=1e-8, check_every=0, ctx=None, out=None):
+    """Poisson-type front end (``xinv_std2d_rows``): the user's forcing ``F_user[..., ny, nx]`` (host
+    numpy array or CUDA tensor; cells equal to ``user_undef`` -- any NaN when that is NaN -- are
+    land), per-row coefficients ``A_rows[ny]``, ``C_rows[ny]`` and an optional per-row forcing scale;
+    returns ``(S, flags[batch, 3], stats)`` with ``S`` solved from a zero initial guess and land set
+    to ``out_undef``.  What apps.__mask_FS / __coeffs_Poisson / __template's de-masking do on the
+    host (apps.py:2112-2159, :1397-1437, :1386-1392) happens on the device; results are identical.
+    Raises ``XinvError`` (code -5) when the fused engine cannot take the problem."""
+    L = _lib.load()
+    ctx = ctx or _lib.default_context()
+    device = _is_device_array(F_user)
+    if device:
+        import torch
+        if F_user.dtype != torch.float64 or not F_user.is_contiguous():
+            raise ValueError("device forcing must be a contiguous float64 tensor")
+        shape = tuple(F_user.shape)
+        S = out if out is not None else torch.empty_like(F_user)
+        rows = [torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64)).to(F_user.device) if v is not None else None
+                for v in (A_rows, C_rows, F_row_scale)]
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        F_ptr, S_ptr = ptr(F_user), ptr(S)
+        keep = rows
+    else:
+        Fh = _host_f64(F_user, "F")
+        shape = Fh.shape
+        S = out if out is not None else np.empty(shape, dtype=np.float64)
+        if S.dtype != np.float64 or not S.flags["C_CONTIGUOUS"] or S.shape != shape:
+            raise ValueError("out must be a C-contiguous float64 array of the forcing's shape")
+        rows = [np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
+                for v in (A_rows, C_rows, F_row_scale)]
+        ptr = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+        F_ptr, S_ptr = ptr(Fh), ptr(S)
+        keep = rows + [Fh]
+    if len(shape) < 2:
+        raise ValueError("forcing needs at least 2 dimensions")
+    ny, nx = int(shape[-2]), int(shape[-1])
+    batch = int(np.prod(shape[:-2], dtype=np.int64)) if len(shape) > 2 else 1
+    for v, name in ((rows[0], "A_rows"), (rows[1], "C_rows"), (rows[2], "F_row_scale")):
+        if v is not None and tuple(v.shape) != (ny,):
+            raise ValueError(f"{name} must have shape ({ny},)")
+    opts = _lib.make_opts(mem_space=_lib.MEM_DEVICE if device else _lib.MEM_HOST, check_every=check_every)
+    fl = _flags_array(flags, batch)
+    rc = L.xinv_std2d_rows(ctx.handle, S_ptr, ptr(rows[0]), ptr(rows[1]), F_ptr, ptr(rows[2]),
+                           float(user_undef), float(out_undef), batch, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
+                           float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
+                           C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance), C.byref(opts))
+    del keep
+    _lib.check(rc)
+    return S, fl, ctx.stats()
+
+
 def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ratioQtr,
                      ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
                      tolerance=1e-8, ordering="colour", engine="auto", check_every=0, ctx=None, profile=False):
