@@ -198,19 +198,39 @@ def make_opts(ordering="colour", mem_space=MEM_HOST, engine="auto", check_every=
 
 
 class _PinnedBlock:
-    """Owner of one cudaHostAlloc block; numpy views keep it alive via .base."""
+    """Owner of one cudaHostAlloc block; numpy views keep it alive via .base.  When the last view
+    goes away the block returns to a small pool instead of being unpinned: page-locking tens of
+    megabytes costs milliseconds, and result arrays of repeated solves have the same size."""
+    _pool = {}                     # nbytes -> [ptr, ...]
+    _pooled_bytes = 0
+    POOL_LIMIT = 2 << 30           # at most 2 GiB of idle pinned memory is kept
 
     def __init__(self, nbytes):
-        p = _vp()
-        check(load().xinv_host_alloc(C.byref(p), int(nbytes)))
-        self.ptr = p.value
-        self.__array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+        nbytes = int(nbytes)
+        free = _PinnedBlock._pool.get(nbytes)
+        if free:
+            self.ptr = free.pop()
+            _PinnedBlock._pooled_bytes -= nbytes
+        else:
+            p = _vp()
+            check(load().xinv_host_alloc(C.byref(p), nbytes))
+            self.ptr = p.value
+        self.nbytes = nbytes
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1",
                                     "data": (self.ptr, False), "version": 3}
 
     def __del__(self):
-        if getattr(self, "ptr", None) and _lib is not None:
-            _lib.xinv_host_free(_vp(self.ptr))
-            self.ptr = None
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if not ptr or _lib is None:
+            return
+        try:
+            if _PinnedBlock._pooled_bytes + self.nbytes <= _PinnedBlock.POOL_LIMIT:
+                _PinnedBlock._pool.setdefault(self.nbytes, []).append(ptr)
+                _PinnedBlock._pooled_bytes += self.nbytes
+            else:
+                _lib.xinv_host_free(_vp(ptr))
+        except Exception:
+            pass
 
 
 def pinned_empty(shape, dtype=np.float64):

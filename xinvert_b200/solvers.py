@@ -177,7 +177,8 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
     else:
         Fh = _host_f64(F_user, "F")
         shape = Fh.shape
-        S = out if out is not None else np.empty(shape, dtype=np.float64)
+        # (page-locked and pooled: the device-to-host copy of the result runs at full PCIe rate)
+        S = out if out is not None else _lib.pinned_empty(shape)
         if S.dtype != np.float64 or not S.flags["C_CONTIGUOUS"] or S.shape != shape:
             raise ValueError("out must be a C-contiguous float64 array of the forcing's shape")
         rows = [np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
