@@ -699,6 +699,11 @@ extern "C" int xinv_end(xinv_ctx *c)
     }
     c->stats.cell_updates = updates;
     c->stats.sweep_ms = max_done ? c->stats.solve_ms / (double)max_done : 0.0;
+    if (pb.profile && pb.engine == XINV_ENGINE_FUSED && pb.ordering != XINV_ORDER_LEX && pb.fused.T > 0) {
+        // passes that did work: the chunks were timed as a whole and may end with passes that found every
+        // slice stopped (a few microseconds each, left in dom_ms); count only the real ones
+        c->stats.dom_launches = (max_done + pb.fused.T - 1) / pb.fused.T;
+    }
     fused_plan_release(pb.fused);
     return XINV_OK;
 }
