@@ -335,7 +335,7 @@ def run_ours(args):
     Fda = (xb.DataArray(hz, ['time', 'lat', 'lon'], dict(coords, time=np.arange(nb))) if nb > 1
            else xb.DataArray(hz, ['lat', 'lon'], coords))
     ipa = {'BCs': list(bcs), 'optArg': p["optArg"], 'mxLoop': sweeps - 1, 'tolerance': -1.0, 'printInfo': False,
-           'ctx': ctx}
+           'ctx': ctx, 'engine': args.engine}
     xb.invert_Poisson(Fda, dims=['lat', 'lon'], iParams=dict(ipa))
     barrier()
     ctx.timer_start()
@@ -343,7 +343,7 @@ def run_ours(args):
         xb.invert_Poisson(Fda, dims=['lat', 'lon'], iParams=dict(ipa))
     ev_api = ctx.timer_stop() / 1e3
     st_a = ctx.stats()
-    assert st_a["engine"] == "fused" and st_a["sweeps_launched"] * st_a["iters_per_pass"] >= sweeps
+    assert st_a["sweeps_launched"] * st_a["iters_per_pass"] >= sweeps
     api = {"ev_s": ev_api, "h2d": st_a["h2d_bytes"], "d2h": st_a["d2h_bytes"], "h2d_ms": st_a["h2d_ms"],
            "d2h_ms": st_a["d2h_ms"]}
     barrier()
