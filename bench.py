@@ -379,12 +379,16 @@ def run_ours(args):
         # so only those bytes are claimed (SURVEY.md 8d rule: never claim bytes that were not needed)
         alg_bytes = 24.0 * N * per_gpu
         kern = f"fused kernel, {st['iters_per_pass']} red+black iterations per pass, row coefficients (psi r+w, F)"
+        limiter = ("FP64 issue: per ncu (profiles/r01_v3_fused_rc_ncu_full.txt) the FP64 pipe is 48 % busy, issue slots "
+                   "63 %, DRAM 38 %; 68 of 167 warp-instructions per row step are FP64 and hold the pipe 2 cycles each")
     elif engine_used == "fused":
         alg_bytes = 40.0 * N * per_gpu          # one pass: S r+w, A, C, F once
         kern = f"fused kernel, {st['iters_per_pass']} red+black iterations per pass (psi r+w, A, C, F)"
+        limiter = "HBM: the kernel moves 48 N bytes per pass (+ the precomputed factor array) at ~5.3 TB/s, DRAM 65 % busy per ncu"
     else:
         alg_bytes = 32.0 * N * per_gpu          # one colour sweep: S 8N r + 4N w, A 8N, C 8N, F 4N
         kern = "colour sweep kernel (one launch per colour)"
+        limiter = "HBM latency: DRAM 72 % busy, long_scoreboard 73 % of warp states per ncu"
     achieved = (alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9) if dom_n else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel from the committed
     # `ncu --set full` capture (profiles/traffic.json; C2 workload, one slice per GPU)
@@ -398,7 +402,7 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": kern, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernel": kern, "limiter": limiter, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "avg_launch_us": (dom_ms / dom_n * 1e3) if dom_n else None, "timed_launches": dom_n}
 
     # ---- CPU baseline: bounded sample of the same workload on one host core ----
