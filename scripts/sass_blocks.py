@@ -3,9 +3,9 @@
 instruction mix -- the FAST row steps are the branch-free regions holding 4 LDS.128 per row.
    python scripts/sass_blocks.py 2,4,3,4,2"""
 import collections, re, subprocess, sys
-T, R, K, NW, MB, CI = sys.argv[1].split(",")
+T, R, K, NW, MB, CI, RC, KD, SW = sys.argv[1].split(",")
 txt = subprocess.run(["cuobjdump", "-sass", "xinvert_b200/libxinv_b200.so"], capture_output=True, text=True).stdout
-pat = f"xm_std2d_kernelILi{T}ELi{R}ELi{K}ELi{NW}ELi{MB}ELb{CI}E"
+pat = f"xm_std2d_kernelILi{T}ELi{R}ELi{K}ELi{NW}ELi{MB}ELb{CI}ELb{RC}ELi{KD}ELb{SW}E"
 ins, on = [], False
 for line in txt.splitlines():
     if "Function :" in line:
