@@ -15,4 +15,4 @@ for w in ("c2", "c5", "ref"):
     except Exception as e:
         print(w, "ERR", e)
 PY
-tail -3 $OUT/*.err | tail -12
+for f in $OUT/*.err; do tail -n 2 $f; done
