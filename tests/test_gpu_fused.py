@@ -35,7 +35,7 @@ def _check(c, bcy, bcx, sweeps, tol=-1.0, omega=1.4, rc=None):
 
 
 VARIANTS = ["0", "1", "2", "3", "4"]          # general kernels (xinv_march2d.cuh: XM_VARIANTS)
-RC_VARIANTS = ["0", "1", "2", "3", "4", "5"]  # RC kernels (XM_RC_VARIANTS; 2, 3, 5 keep the records in shared memory)
+RC_VARIANTS = ["0", "1", "2", "3", "4", "5", "6"]  # RC kernels (XM_RC_VARIANTS; 2, 3, 5, 6 keep the records in shared memory; 6: T = 4)
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -72,7 +72,7 @@ def test_fused_rowcoef_equals_general_kernels(gpu_ctx, monkeypatch):
     _check(c, "extend", "periodic", 7, rc=False)
 
 
-@pytest.mark.parametrize("variant", ["0", "2", "3", "4"])
+@pytest.mark.parametrize("variant", ["0", "2", "3", "4", "6"])
 @pytest.mark.parametrize("rb", ["1", "3", "8", "17"])
 @pytest.mark.parametrize("bcy,bcx", BCS)
 def test_fused_many_strips(gpu_ctx, monkeypatch, variant, rb, bcy, bcx):
@@ -89,7 +89,7 @@ def test_fused_many_strips(gpu_ctx, monkeypatch, variant, rb, bcy, bcx):
 
 
 @pytest.mark.parametrize("rcflag", ["0", "1"])
-@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("variant", VARIANTS + ["6"])
 def test_fused_poisson_to_tolerance(gpu_ctx, monkeypatch, variant, rcflag):
     monkeypatch.setenv("XINV_FUSED_VARIANT", variant)
     monkeypatch.setenv("XINV_FUSED_RC_VARIANT", variant)
@@ -100,7 +100,7 @@ def test_fused_poisson_to_tolerance(gpu_ctx, monkeypatch, variant, rcflag):
 
 
 @pytest.mark.parametrize("rcflag", ["0", "1"])
-@pytest.mark.parametrize("variant", ["1", "2", "3"])
+@pytest.mark.parametrize("variant", ["1", "2", "3", "6"])
 def test_fused_t2_redo_when_stopping_mid_pass(gpu_ctx, monkeypatch, variant, rcflag):
     """T = 2: tolerances chosen so that the stop test fires after the 1st and after the
     2nd iteration of a pass (even and odd sweep counts); the overshoot is rolled back."""

@@ -494,7 +494,8 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     CK(cudaMemcpyAsync(ftmp.p, a.flags, sizeof(double) * 3 * a.batch, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->ticket.p, 0, sizeof(unsigned) * a.batch, c->stream));
     {
-        const int nit0 = (pb.engine == XINV_ENGINE_FUSED && pb.fused.T > 1 && a.mxLoop >= 1) ? pb.fused.T : 1;
+        // iterations of the first pass: T, but never more sweeps than mxLoop allows (loop = 0 .. mxLoop)
+        const int nit0 = (pb.engine == XINV_ENGINE_FUSED) ? (int)((a.mxLoop + 1 < (i64)pb.fused.T) ? a.mxLoop + 1 : (i64)pb.fused.T) : 1;
         xd_init_state_kernel<<<(unsigned)((a.batch + 127) / 128), 128, 0, c->stream>>>(
             (XdSliceState *)c->state.p, (const double *)ftmp.p, (int)a.batch, (int *)c->nactive.p, nit0);
     }
