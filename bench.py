@@ -254,7 +254,7 @@ def run_ours(args):
     N = ny * nx
     sweeps = args.sweeps
     kw = dict(undef=UNDEF, mxLoop=sweeps - 1, tolerance=-1.0, ctx=ctx, engine=args.engine)
-    if world > 1:
+    if world > 1 or args.chunk != 128:
         # ranks exchange their active-slice counts (one scalar all-reduce) after every chunk of passes;
         # ~6 ms of device work per chunk keeps that exchange below 1 % of the step
         kw["sweeps_per_chunk"] = args.chunk
