@@ -273,3 +273,28 @@ def test_poisson_device_front_end_falls_back(gpu_ctx):
     s = xb.invert_Poisson(F, dims=['lat', 'lon'], iParams=dict(ip))
     s_o = _via_oracle(xb.invert_Poisson, F, dims=['lat', 'lon'], iParams=dict(ip))
     assert np.array_equal(s.values, s_o.values, equal_nan=True)
+
+
+def test_front_end_with_device_tensors(gpu_ctx):
+    """solve_standard_2D_rows with the forcing already on the device (CUDA tensor in, CUDA tensor out)."""
+    import torch
+    ny, nx = 64, 128
+    zeta, lat, lon = cases_user(ny, nx)
+    lats = np.deg2rad(lat)
+    cosG = np.cos(lats)
+    latm = np.empty(ny); latm[0] = np.nan; latm[1:] = lats[:-1]
+    A_rows, C_rows = np.cos((lats + latm) / 2.0), 1.0 / cosG
+    from tests import cases
+    p = cases.params2d(ny, nx, np.deg2rad(180.0 / ny) * cases.REARTH, np.deg2rad(360.0 / nx) * cases.REARTH)
+    args = (A_rows, C_rows, cosG, np.nan, np.nan, "extend", "periodic", p["del1Sqr"], p["ratioQtr"], p["ratioSqr"], 1.4)
+    S_h, fl_h, _ = xb.solve_standard_2D_rows(zeta, *args, mxLoop=300, tolerance=1e-8)
+    Fd = torch.from_numpy(zeta).to("cuda:0")
+    S_d, fl_d, st = xb.solve_standard_2D_rows(Fd, *args, mxLoop=300, tolerance=1e-8)
+    assert st["h2d_bytes"] == 0 and st["d2h_bytes"] == 0
+    assert np.array_equal(S_d.cpu().numpy(), S_h, equal_nan=True) and np.array_equal(fl_d, fl_h)
+    assert np.isnan(S_h[np.isnan(zeta)]).all() and np.isfinite(S_h[~np.isnan(zeta)]).all()
+
+
+def cases_user(ny, nx):
+    from tests import cases
+    return cases.poisson_latlon_user(ny, nx, land=True, noise=1e-6, seed=3)

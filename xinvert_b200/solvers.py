@@ -171,6 +171,7 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
         S = out if out is not None else torch.empty_like(F_user)
         rows = [torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64)).to(F_user.device) if v is not None else None
                 for v in (A_rows, C_rows, F_row_scale)]
+        torch.cuda.current_stream(F_user.device).synchronize()    # the row vectors were copied on torch's stream
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         F_ptr, S_ptr = ptr(F_user), ptr(S)
         keep = rows
