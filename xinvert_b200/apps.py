@@ -295,10 +295,12 @@ def _mask_FS(g, iParams, icbc):
     else:
         maskF = np.where(v != iParams['undef'], v, _undeftmp)
     maskF = maskF.astype(np.result_type(v.dtype, np.float32), copy=False)
-    zero = maskF - maskF
-    zero_is_zero = not np.any(zero != 0)        # NaN != 0 is True: catches inf/NaN forcings
+    # `zero = maskF - maskF` is identically zero unless the forcing holds an inf or an unmasked NaN
+    # (then those cells turn every coefficient into NaN: a quirk the full-size path reproduces)
+    zero_is_zero = bool(np.isfinite(maskF).all())
+    zero = np.zeros_like(maskF) if zero_is_zero else maskF - maskF
     if icbc is None:
-        initS = zero.copy()
+        return maskF, (np.zeros_like(maskF) if zero_is_zero else zero.copy()), zero, zero_is_zero
     else:
         mask = (maskF == _undeftmp)
         for k, BC in enumerate(iParams['BCs']):
@@ -589,9 +591,9 @@ def _template(coef_func, inv_func, dimLen, F, dims, coords='lat-lon', icbc=None,
     inv_func(*coeffs, Ff, S, dims, iParams)
 
     ######  4. properly de-masking  ######
-    out = np.asarray(S.values)
+    out = np.asarray(S.values)                   # our own array (built from initS), free to modify
     if icbc is None:
-        out = np.where(maskF != _undeftmp, out, iParams['undef'])
+        out[maskF == _undeftmp] = iParams['undef']
     if np.asarray(F.values).dtype == np.float32:
         out = out.astype(np.float32)
     return wrap_like(F, out, name='inverted')

@@ -83,7 +83,10 @@ def _finish(S, result, order, iParams, labels, flags):
     inv = np.argsort(order)
     out = np.transpose(result, inv)
     sv = S.values
-    sv[...] = out.astype(sv.dtype, copy=False)
+    same = (isinstance(sv, np.ndarray) and out.shape == sv.shape and out.strides == sv.strides and out.dtype == sv.dtype
+            and out.__array_interface__['data'][0] == sv.__array_interface__['data'][0])
+    if not same:                                # (the solve ran in place on S.values when no re-layout was needed)
+        sv[...] = out.astype(sv.dtype, copy=False)
     iParams["flags_all"] = flags
     fl = iParams.get("flags")
     if isinstance(fl, np.ndarray) and fl.shape == (3,):
