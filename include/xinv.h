@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define XINV_VERSION 101
+#define XINV_VERSION 102
 
 /* boundary conditions (numbas.py BCy/BCx strings 'fixed' / 'extend' / 'periodic') */
 #define XINV_BC_FIXED    0
@@ -153,6 +153,18 @@ int xinv_std2d_rows(xinv_ctx *ctx, double *S_out, const double *A_rows, const do
                     const double *F_user, const double *F_row_scale, double user_undef, double out_undef,
                     int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
                     double delxSqr, double ratioQtr, double ratioSqr,
+                    double optArg, double undef, double *flags,
+                    int64_t mxLoop, double tolerance, const xinv_opts *opts);
+
+/* The same front end for the general form with coefficients constant along x (invert_GillMatsuno,
+ * invert_Stommel; apps.py:1609-1657, :1712-1748): rows = [5][ny] = A, C, D, E, F of every row;
+ * G_user the user's forcing (user_undef / NaN = land).  g_mode 0: G = forcing (Gill-Matsuno,
+ * apps.py:1655); g_mode 1: G = ((-forcing) / g_p1) / g_p2 (Stommel: -curl / D / rho0, apps.py:1746).
+ * S_out is output only (zero initial guess), land is set to out_undef.  XINV_E_UNSUPPORTED as above. */
+int xinv_gen2d_rows(xinv_ctx *ctx, double *S_out, const double *rows, const double *G_user,
+                    int g_mode, double g_p1, double g_p2, double user_undef, double out_undef,
+                    int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                    double delx, double delxSqr, double ratio, double ratioQtr, double ratioSqr,
                     double optArg, double undef, double *flags,
                     int64_t mxLoop, double tolerance, const xinv_opts *opts);
 

@@ -19,7 +19,7 @@ def test_library_builds_and_loads():
     path = build.build()
     assert os.path.exists(path)
     L = _lib.load()
-    assert L.xinv_version() == 101
+    assert L.xinv_version() == 102
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -298,3 +298,44 @@ def test_front_end_with_device_tensors(gpu_ctx):
 def cases_user(ny, nx):
     from tests import cases
     return cases.poisson_latlon_user(ny, nx, land=True, noise=1e-6, seed=3)
+
+
+@pytest.mark.parametrize("model", ["GillMatsuno-latlon", "GillMatsuno-cartesian", "Stommel-cartesian", "Stommel-latlon"])
+def test_general_form_device_front_end_equals_host_path(gpu_ctx, monkeypatch, model):
+    """invert_GillMatsuno / invert_Stommel with icbc=None go through xinv_gen2d_rows; the host path must
+    give the same bits (land marked by NaN and by a value, batched over a time axis)."""
+    from xinvert_b200 import apps
+    ny, nx, T = 60, 120, 2
+    rng = np.random.default_rng(9)
+    if model.endswith("latlon"):
+        co = {'lat': np.linspace(-59, 59, ny), 'lon': np.linspace(0, 357, nx)}
+        coords = 'lat-lon'
+    else:
+        co = {'lat': np.linspace(-3e6, 3e6, ny), 'lon': np.linspace(0, 2e7, nx, endpoint=False)}
+        coords = 'cartesian'
+    yy, xx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    q = np.stack([(1 + t) * 0.05 * np.exp(-((yy - 30) ** 2 + (xx - 60) ** 2) / 50.0) + 1e-4 * rng.standard_normal((ny, nx))
+                  for t in range(T)])
+    land = (np.abs(yy - 20) < 3) & (np.abs(xx - 30) < 10)
+    if model.startswith("Gill"):
+        fn, mp = xb.invert_GillMatsuno, {'epsilon': 1e-5, 'Phi': 5000, 'f0': 0.0, 'beta': 2e-11}
+    else:
+        fn, mp = xb.invert_Stommel, {'beta': 2e-11, 'R': 5e-4, 'D': 200}
+        q = q * 1e-9
+    for undef in (np.nan, -9999.0):
+        qq = q.copy()
+        qq[:, land] = undef
+        F = DA(qq, ['time', 'lat', 'lon'], dict(co, time=np.arange(T)))
+        ip = {'BCs': ['fixed', 'periodic'], 'tolerance': 1e-9, 'mxLoop': 400, 'optArg': 1.4, 'undef': undef, 'printInfo': False}
+        calls = []
+        real = apps._device_solvers.solve_general_2D_rows
+        monkeypatch.setattr(apps._device_solvers, "solve_general_2D_rows", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+        s_f = fn(F, dims=['lat', 'lon'], coords=coords, iParams=dict(ip), mParams=mp)
+        assert calls, "the device front end was not used"
+        monkeypatch.setattr(apps, "_general_device_front", lambda *a, **k: None)
+        s_h = fn(F, dims=['lat', 'lon'], coords=coords, iParams=dict(ip), mParams=mp)
+        monkeypatch.undo()
+        assert np.array_equal(s_f.values, s_h.values, equal_nan=True)
+        lv = s_f.values[:, land]
+        assert np.isnan(lv).all() if np.isnan(undef) else (lv == undef).all()
+        assert np.isfinite(s_f.values[:, ~land]).all() and np.abs(s_f.values[:, ~land]).max() > 0

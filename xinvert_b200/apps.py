@@ -96,6 +96,10 @@ def invert_GillMatsuno(Q, dims, coords='lat-lon', icbc=None,
                        mParams=default_mParams, iParams=default_iParams):
     r"""Invert the Gill-Matsuno model for the mass field :math:`\phi` given the
     heating ``Q`` (apps.py:349-394); winds follow from ``cal_flow``."""
+    valid = ['f0', 'beta', 'epsilon', 'Phi', 'g', 'Omega', 'Rearth']
+    fast = _general_device_front(_rows_GillMatsuno, valid, Q, dims, coords, icbc, mParams, iParams)
+    if fast is not None:
+        return fast
     return _template(_coeffs_GillMatsuno, core.inv_general2D, 2, Q, dims, coords,
                      icbc, ['f0', 'beta', 'epsilon', 'Phi', 'g', 'Omega', 'Rearth'],
                      mParams, iParams)
@@ -105,6 +109,10 @@ def invert_Stommel(curl, dims, coords='lat-lon', icbc=None,
                    mParams=default_mParams, iParams=default_iParams):
     r"""Invert the Stommel model for the streamfunction given the wind-stress
     curl (apps.py:445-488)."""
+    valid = ['beta', 'R', 'D', 'rho0', 'g', 'Omega', 'Rearth']
+    fast = _general_device_front(_rows_Stommel, valid, curl, dims, coords, icbc, mParams, iParams)
+    if fast is not None:
+        return fast
     return _template(_coeffs_Stommel, core.inv_general2D, 2, curl, dims, coords,
                      icbc, ['beta', 'R', 'D', 'rho0', 'g', 'Omega', 'Rearth'],
                      mParams, iParams)
@@ -440,12 +448,12 @@ def _coeffs_Eliassen(g, coords, mParams, iParams, icbc):
     return maskF, Fm, initS, (A, B, C)
 
 
-def _coeffs_GillMatsuno(g, coords, mParams, iParams, icbc):
-    """apps.__coeffs_GillMatsuno (apps.py:1609-1657)."""
+def _rows_GillMatsuno(g, coords, mParams):
+    """The coefficients of apps.__coeffs_GillMatsuno (apps.py:1609-1657) as functions of the first core
+    dim: A, C, D, E (vectors) and F (a constant); the forcing is used as it is (g_mode 0)."""
     Phi, epsilon = mParams['Phi'], mParams['epsilon']
     f0, beta = mParams['f0'], mParams['beta']
     Omega, Rearth = mParams['Omega'], mParams['Rearth']
-    maskF, initS, zero, z0 = _mask_FS(g, iParams, icbc)
     ydef = np.asarray(g.coord(0), dtype=np.float64)
     c = coords.lower()
     if c == 'lat-lon':
@@ -471,37 +479,88 @@ def _coeffs_GillMatsuno(g, coords, mParams, iParams, icbc):
         tE = - Phi * np.gradient(c2, ydef, edge_order=1)
     else:
         raise Exception('unsupported coords ' + coords + ', should be in [lat-lon, cartesian]')
-    A = _coef(g, zero, z0, lambda full: g.along(0, tA, full))
+    return dict(A=tA, C=tC, D=tD, E=tE, F=-epsilon, g_mode=0, g_p1=1.0, g_p2=1.0)
+
+
+def _coeffs_GillMatsuno(g, coords, mParams, iParams, icbc):
+    """apps.__coeffs_GillMatsuno (apps.py:1609-1657)."""
+    r = _rows_GillMatsuno(g, coords, mParams)
+    maskF, initS, zero, z0 = _mask_FS(g, iParams, icbc)
+    A = _coef(g, zero, z0, lambda full: g.along(0, r['A'], full))
     B = _Field(zero, g.all_dims) if not z0 else _Field(np.zeros(g.core_shape), g.dims)
-    C = _coef(g, zero, z0, lambda full: g.along(0, tC, full))
-    D = _coef(g, zero, z0, lambda full: g.along(0, tD, full))
-    E = _coef(g, zero, z0, lambda full: g.along(0, tE, full))
-    F = _coef(g, zero, z0, lambda full: -epsilon)
+    C = _coef(g, zero, z0, lambda full: g.along(0, r['C'], full))
+    D = _coef(g, zero, z0, lambda full: g.along(0, r['D'], full))
+    E = _coef(g, zero, z0, lambda full: g.along(0, r['E'], full))
+    F = _coef(g, zero, z0, lambda full: r['F'])
     G = np.where(maskF != _undeftmp, maskF, _undeftmp)
     return maskF, G, initS, (A, B, C, D, E, F)
 
 
-def _coeffs_Stommel(g, coords, mParams, iParams, icbc):
-    """apps.__coeffs_Stommel (apps.py:1712-1748)."""
+def _rows_Stommel(g, coords, mParams):
+    """apps.__coeffs_Stommel (apps.py:1712-1748) along the first core dim: A, C, E (B = D = F = 0) and the
+    forcing transform G = -curl / D / rho0 (g_mode 1)."""
     beta, R, depth, rho0 = mParams['beta'], mParams['R'], mParams['D'], mParams['rho0']
     Rearth, Omega = mParams['Rearth'], mParams['Omega']
-    maskF, initS, zero, z0 = _mask_FS(g, iParams, icbc)
     c = coords.lower()
     if c == 'lat-lon':
         cosL = np.cos(np.deg2rad(g.coord(0)))
-        A = _coef(g, zero, z0, lambda full: - R / depth)
-        C = _coef(g, zero, z0, lambda full: g.along(0, - R / depth / cosL ** 2., full))
-        E = _coef(g, zero, z0, lambda full: - 2. * Omega / Rearth)
+        tA, tC, tE = - R / depth, - R / depth / cosL ** 2., - 2. * Omega / Rearth
     elif c == 'cartesian':
-        A = _coef(g, zero, z0, lambda full: - R / depth)
-        C = _coef(g, zero, z0, lambda full: - R / depth)
-        E = _coef(g, zero, z0, lambda full: - beta)
+        tA, tC, tE = - R / depth, - R / depth, - beta
     else:
         raise Exception('unsupported coords ' + coords + ', should be in [lat-lon, z-lat, z-lon, cartesian]')
+    return dict(A=tA, C=tC, D=0.0, E=tE, F=0.0, g_mode=1, g_p1=depth, g_p2=rho0)
+
+
+def _coeffs_Stommel(g, coords, mParams, iParams, icbc):
+    """apps.__coeffs_Stommel (apps.py:1712-1748)."""
+    r = _rows_Stommel(g, coords, mParams)
+    depth, rho0 = mParams['D'], mParams['rho0']
+    maskF, initS, zero, z0 = _mask_FS(g, iParams, icbc)
+    vec = lambda v: (lambda full: g.along(0, v, full)) if np.ndim(v) else (lambda full: v)
+    A = _coef(g, zero, z0, vec(r['A']))
+    C = _coef(g, zero, z0, vec(r['C']))
+    E = _coef(g, zero, z0, vec(r['E']))
     zf = _Field(zero, g.all_dims) if not z0 else _Field(np.zeros(g.core_shape), g.dims)
     B, D, F = zf, zf, zf
     G = np.where(maskF != _undeftmp, -maskF / depth / rho0, _undeftmp)
     return maskF, G, initS, (A, B, C, D, E, F)
+
+
+def _general_device_front(rows_func, valid, F, dims, coords, icbc, mParams, iParams):
+    """invert_GillMatsuno / invert_Stommel through the device-side front end (``xinv_gen2d_rows``), or
+    None when the reference-shaped host path has to be taken (see _poisson_device_front)."""
+    if icbc is not None or len(dims) != 2:
+        return None
+    ip = _update(default_iParams, iParams)
+    if ip.get('ordering', 'colour') not in ('colour', 'color', 'redblack', 'red-black') or \
+            ip.get('engine', 'auto') == 'colour' or core.solvers is not _device_solvers:
+        return None
+    mp = _update(default_mParams, mParams, valid)
+    g = _Grid(F, dims)
+    if not g.trailing or g.values.dtype != np.float64 or coords.lower() not in ('lat-lon', 'cartesian'):
+        return None
+    r = rows_func(g, coords, mp)
+    ny = g.core_shape[0]
+    rows = np.stack([np.broadcast_to(np.asarray(r[k], dtype=np.float64), (ny,)) for k in 'ACDEF'])
+    ps = _cal_params2D(g, coords, mp['Rearth'])
+    ip = _update(ps, ip)
+    if ip['debug']:
+        _print_params(ip)
+    try:
+        S, flags, _ = _device_solvers.solve_general_2D_rows(
+            g.values, rows, r['g_mode'], r['g_p1'], r['g_p2'], ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1],
+            ip['del1'], ip['del1Sqr'], ip['ratio'], ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp,
+            ip['flags'], ip['mxLoop'], ip['tolerance'], ctx=ip.get('ctx'))
+    except XinvError as e:
+        if 'error -5' in str(e):                 # XINV_E_UNSUPPORTED: not a problem for the fused engine
+            return None
+        raise
+    _, noncore, _ = core._layout(F, dims)
+    core._report(ip, core._slice_labels(F, noncore), flags)
+    if isinstance(iParams, dict):
+        iParams['flags_all'] = flags
+    return wrap_like(F, S, name='inverted')
 
 
 def _coeffs_omega(g, coords, mParams, iParams, icbc):

@@ -312,6 +312,9 @@ struct BeginArgs {
     bool front = false;
     const double *f_scale = nullptr;
     double user_undef = 0.0, out_undef = 0.0;
+    // xinv_gen2d_rows: coef[0] = rows [5][ny], coef[6] = user forcing
+    int g_mode = 0;
+    double g_p1 = 1.0, g_p2 = 1.0;
 };
 
 static int problem_begin(xinv_ctx *c, const BeginArgs &a)
@@ -394,7 +397,29 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
         front.user_undef = a.user_undef;
         front.out_undef = a.out_undef;
         const size_t row_bytes = (size_t)a.ny * sizeof(double);
-        if (pb.mem_space == XINV_MEM_HOST) {
+        const bool gen = (a.kind == XD_GEN2D);
+        front.g_mode = a.g_mode; front.g_p1 = a.g_p1; front.g_p2 = a.g_p2;
+        if (gen && pb.mem_space == XINV_MEM_HOST) {
+            CK(cudaEventRecord(e0, c->stream));
+            int rc = ensure(c->stage[0], slice_bytes * a.batch);            // S (device only until xinv_end)
+            if (rc) return rc;
+            if ((rc = ensure(c->stage[2 + 6], slice_bytes * a.batch))) return rc;   // user forcing
+            if ((rc = ensure(c->stage[2 + 0], 5 * row_bytes))) return rc;           // A, C, D, E, F rows
+            CK(cudaMemcpyAsync(c->stage[8].p, a.coef[6], slice_bytes * a.batch, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->stage[2].p, a.coef[0], 5 * row_bytes, cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2d_bytes += (i64)(slice_bytes * a.batch + 5 * row_bytes);
+            CK(cudaEventRecord(e1, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            c->stats.h2d_ms = ms;
+            pb.dS = (double *)c->stage[0].p;
+            front.F = (const double *)c->stage[8].p;
+            front.rows5 = (const double *)c->stage[2].p;
+        } else if (gen) {
+            pb.dS = a.S;
+            front.F = a.coef[6]; front.rows5 = a.coef[0];
+        } else if (pb.mem_space == XINV_MEM_HOST) {
             CK(cudaEventRecord(e0, c->stream));
             int rc = ensure(c->stage[0], slice_bytes * a.batch);            // S (device only until xinv_end)
             if (rc) return rc;
@@ -755,6 +780,28 @@ extern "C" int xinv_std2d_rows(xinv_ctx *ctx, double *S_out, const double *A_row
     a.p[0] = delxSqr; a.p[1] = ratioQtr; a.p[2] = ratioSqr;
     a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
     a.front = true; a.f_scale = F_row_scale; a.user_undef = user_undef; a.out_undef = out_undef;
+    int rc = problem_begin(ctx, a);
+    if (rc) return rc;
+    return run_to_completion(ctx);
+}
+
+extern "C" int xinv_gen2d_rows(xinv_ctx *ctx, double *S_out, const double *rows, const double *G_user,
+                               int g_mode, double g_p1, double g_p2, double user_undef, double out_undef,
+                               int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                               double delx, double delxSqr, double ratio, double ratioQtr, double ratioSqr,
+                               double optArg, double undef, double *flags,
+                               int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    BeginArgs a{};
+    a.kind = XD_GEN2D; a.S = S_out;
+    for (int m = 0; m < 7; ++m) a.coef[m] = rows;          // only [0] (the row block) and [6] (forcing) are used
+    a.coef[1] = nullptr; a.coef[6] = G_user; a.ncoef = 7; a.b_index = 1;
+    a.batch = batch; a.nz = 1; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delx; a.p[1] = delxSqr; a.p[2] = ratio; a.p[3] = ratioQtr; a.p[4] = ratioSqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    a.front = true; a.user_undef = user_undef; a.out_undef = out_undef;
+    a.g_mode = g_mode; a.g_p1 = g_p1; a.g_p2 = g_p2;
+    if (!rows || !G_user) return set_err(XINV_E_ARG, "rows and G_user must not be NULL");
     int rc = problem_begin(ctx, a);
     if (rc) return rc;
     return run_to_completion(ctx);

@@ -205,6 +205,37 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
     return S, fl, ctx.stats()
 
 
+def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_undef, BCy, BCx, delx, delxSqr, ratio,
+                          ratioQtr, ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
+                          tolerance=1e-8, check_every=0, ctx=None):
+    """General-form front end (``xinv_gen2d_rows``): the user's forcing ``G_user[..., ny, nx]`` (host
+    numpy array), ``rows[5, ny]`` = A, C, D, E, F of every row, and the forcing transform (``g_mode`` 0:
+    G = forcing; 1: G = ((-forcing) / g_p1) / g_p2); returns ``(S, flags[batch, 3], stats)`` with ``S``
+    solved from a zero initial guess and land set to ``out_undef`` (what apps.__mask_FS /
+    __coeffs_GillMatsuno / __coeffs_Stommel / __template do on the host, on the device)."""
+    L = _lib.load()
+    ctx = ctx or _lib.default_context()
+    Gh = _host_f64(G_user, "G")
+    shape = Gh.shape
+    if len(shape) < 2:
+        raise ValueError("forcing needs at least 2 dimensions")
+    ny, nx = int(shape[-2]), int(shape[-1])
+    batch = int(np.prod(shape[:-2], dtype=np.int64)) if len(shape) > 2 else 1
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    if rows.shape != (5, ny):
+        raise ValueError(f"rows must have shape (5, {ny})")
+    S = _lib.pinned_empty(shape)
+    opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
+    fl = _flags_array(flags, batch)
+    rc = L.xinv_gen2d_rows(ctx.handle, C.c_void_p(S.ctypes.data), C.c_void_p(rows.ctypes.data), C.c_void_p(Gh.ctypes.data),
+                           int(g_mode), float(g_p1), float(g_p2), float(user_undef), float(out_undef), batch, ny, nx,
+                           _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delx), float(delxSqr), float(ratio),
+                           float(ratioQtr), float(ratioSqr), float(optArg), float(undef), C.c_void_p(fl.ctypes.data),
+                           int(mxLoop), float(tolerance), C.byref(opts))
+    _lib.check(rc)
+    return S, fl, ctx.stats()
+
+
 def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ratioQtr,
                      ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
                      tolerance=1e-8, ordering="colour", engine="auto", check_every=0, ctx=None, profile=False):
