@@ -88,8 +88,17 @@ _lib = None
 _lock = threading.Lock()
 
 
+# return codes of include/xinv.h
+E_ARG, E_CUDA, E_STATE, E_NOMEM, E_UNSUPPORTED, E_NCCL = -1, -2, -3, -4, -5, -6
+
+
 class XinvError(RuntimeError):
-    """A negative return code of the C-ABI (argument, CUDA or NCCL error)."""
+    """A negative return code of the C-ABI (argument, CUDA or NCCL error); ``.code`` holds it
+    (``E_UNSUPPORTED`` = -5 is what the facade tests for before it falls back to the host-built path)."""
+
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
 
 
 def load():
@@ -110,7 +119,7 @@ def load():
 def check(rc):
     if rc != 0:
         msg = load().xinv_last_error()
-        raise XinvError(f"libxinv_b200 error {rc}: {msg.decode() if msg else ''}")
+        raise XinvError(f"libxinv_b200 error {rc}: {msg.decode() if msg else ''}", code=int(rc))
 
 
 def device_count():
@@ -131,6 +140,10 @@ class Context:
             check(L.xinv_create_on_stream(C.byref(h), int(device), _vp(int(stream))))
         self._h = h
         self.device = int(device)
+        # a ctx holds ONE problem slot and shared staging buffers: every begin..end sequence on it is
+        # serialised (ctypes releases the GIL for the whole solve, so two Python threads -- e.g. the
+        # dask threaded scheduler -- could otherwise interleave on the same ctx)
+        self.lock = threading.RLock()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -167,18 +180,21 @@ class Context:
 
 
 _default_ctx = {}
+_default_ctx_lock = threading.Lock()
 
 
 def default_context(device=0):
-    """Process-wide context per device (created on first use)."""
-    ctx = _default_ctx.get(device)
-    if ctx is None or not ctx._h:
-        if device_count() <= device:
-            raise XinvError(
-                f"no CUDA device {device} visible: xinvert_b200 has no CPU fallback "
-                "(the SOR path runs only as sm_100a CUDA)")
-        ctx = Context(device)
-        _default_ctx[device] = ctx
+    """Process-wide context per device (created on first use).  Calls that share it are serialised by
+    ``Context.lock``; threads that want to overlap their solves create their own ``Context``."""
+    with _default_ctx_lock:
+        ctx = _default_ctx.get(device)
+        if ctx is None or not ctx._h:
+            if device_count() <= device:
+                raise XinvError(
+                    f"no CUDA device {device} visible: xinvert_b200 has no CPU fallback "
+                    "(the SOR path runs only as sm_100a CUDA)")
+            ctx = Context(device)
+            _default_ctx[device] = ctx
     return ctx
 
 

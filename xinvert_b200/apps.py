@@ -30,7 +30,7 @@ import numpy as np
 
 from . import core
 from . import solvers as _device_solvers
-from ._lib import XinvError
+from ._lib import E_UNSUPPORTED, XinvError
 from .xrshim import coord_values, wrap_like
 
 _undeftmp = -9.99e8
@@ -410,13 +410,12 @@ def _poisson_device_front(F, dims, coords, icbc, mParams, iParams):
             ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp, ip['flags'], ip['mxLoop'], ip['tolerance'],
             ctx=ip.get('ctx'))
     except XinvError as e:
-        if 'error -5' in str(e):                 # XINV_E_UNSUPPORTED: not a problem for the fused engine
+        if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
             return None
         raise
     _, noncore, _ = core._layout(F, dims)
     core._report(ip, core._slice_labels(F, noncore), flags)
-    if isinstance(iParams, dict):
-        iParams['flags_all'] = flags
+    _report_flags(iParams, flags)
     return wrap_like(F, S, name='inverted')
 
 
@@ -553,13 +552,12 @@ def _general_device_front(rows_func, valid, F, dims, coords, icbc, mParams, iPar
             ip['del1'], ip['del1Sqr'], ip['ratio'], ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp,
             ip['flags'], ip['mxLoop'], ip['tolerance'], ctx=ip.get('ctx'))
     except XinvError as e:
-        if 'error -5' in str(e):                 # XINV_E_UNSUPPORTED: not a problem for the fused engine
+        if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
             return None
         raise
     _, noncore, _ = core._layout(F, dims)
     core._report(ip, core._slice_labels(F, noncore), flags)
-    if isinstance(iParams, dict):
-        iParams['flags_all'] = flags
+    _report_flags(iParams, flags)
     return wrap_like(F, S, name='inverted')
 
 
@@ -614,6 +612,13 @@ def _coeffs_omega(g, coords, mParams, iParams, icbc):
     return maskF, Fm, initS, (A, B, C)
 
 
+def _report_flags(user_iParams, flags):
+    """Per-slice flags [batch, 3] go back to the caller's own iParams dict (an addition to the
+    reference's interface, the same on every path) -- never into the module-level defaults."""
+    if isinstance(user_iParams, dict) and user_iParams is not default_iParams:
+        user_iParams['flags_all'] = flags
+
+
 def _print_params(iParams):
     for k in sorted(iParams):
         if k not in ('flags_all',):
@@ -626,6 +631,7 @@ def _template(coef_func, inv_func, dimLen, F, dims, coords='lat-lon', icbc=None,
     if len(dims) != dimLen:
         raise Exception('{0:2d} dimensional forcing are needed'.format(dimLen))
 
+    user_iParams = iParams
     iParams = _update(default_iParams, iParams)
     mParams = _update(default_mParams, mParams, validParams)
     g = _Grid(F, dims)
@@ -648,6 +654,8 @@ def _template(coef_func, inv_func, dimLen, F, dims, coords='lat-lon', icbc=None,
     S = wrap_like(F, np.ascontiguousarray(initS, dtype=np.float64))
     Ff = wrap_like(F, forcing)
     inv_func(*coeffs, Ff, S, dims, iParams)
+    if 'flags_all' in iParams:
+        _report_flags(user_iParams, iParams['flags_all'])
 
     ######  4. properly de-masking  ######
     out = np.asarray(S.values)                   # our own array (built from initS), free to modify

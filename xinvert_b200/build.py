@@ -41,16 +41,37 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile the library if it is missing or older than its sources."""
+    """Compile the library if it is missing or older than its sources.  Safe when several processes
+    (one rank per GPU) get here at once: an fcntl lock serialises them, the compiler writes to a
+    temporary file and the finished library is renamed into place, so nobody dlopens a half-written
+    file and only the first process compiles."""
     if not force and not _stale():
         return LIB
-    cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
-           *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB, "-ldl"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libxinv_b200.so:\n" + r.stderr[-4000:])
+    import fcntl
+    try:
+        lockf = open(LIB + ".lock", "w")
+    except OSError:                              # read-only install: nothing to build into
+        if os.path.exists(LIB):
+            return LIB
+        raise
+    try:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        if not force and not _stale():           # another process built it while we waited
+            return LIB
+        tmp = f"{LIB}.tmp.{os.getpid()}"
+        cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
+               *[os.path.join(CSRC, s) for s in SOURCES], "-o", tmp, "-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+            raise RuntimeError("nvcc failed building libxinv_b200.so:\n" + r.stderr[-4000:])
+        os.replace(tmp, LIB)
+    finally:
+        fcntl.flock(lockf, fcntl.LOCK_UN)
+        lockf.close()
     return LIB
 
 

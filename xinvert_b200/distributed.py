@@ -118,6 +118,18 @@ def solve_standard_2D_sharded(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratio
     fl = solvers._flags_array(flags, ops.batch)
     ptrs = [C.c_void_p(ops.S_ptr)] + [C.c_void_p(p) if p is not None else None for p in ops.ptrs]
     L = _lib.load()
+    if ops.device:
+        solvers._sync_torch_stream(S)           # operands produced on torch's stream (S.copy_ ...) are complete
+    ctx.lock.acquire()                           # one begin..end sequence at a time on a ctx
+    try:
+        return _sharded_locked(L, ctx, ptrs, ops, ny, nx, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg, undef, fl,
+                               mxLoop, tolerance, opts, allreduce, sweeps_per_chunk)
+    finally:
+        ctx.lock.release()
+
+
+def _sharded_locked(L, ctx, ptrs, ops, ny, nx, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg, undef, fl, mxLoop,
+                    tolerance, opts, allreduce, sweeps_per_chunk):
     _lib.check(L.xinv_std2d_begin(ctx.handle, *ptrs, ops.batch, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
                                   float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
                                   C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance), C.byref(opts)))

@@ -120,19 +120,56 @@ def _zero_to_none(B):
     return None if not Bn.any() else B
 
 
-def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, profile=False):
+MAX_BATCH = 65535                 # slices per C-ABI call (the slice index rides on a 16-bit grid dimension)
+
+
+def _batch_chunks(batch):
+    """(lo, hi) blocks of at most MAX_BATCH slices: the reference's serial loop takes any number of
+    non-core slices (hourly data x levels easily exceeds 65535), so longer batches are cut here."""
+    if batch <= 0:
+        return [(0, 0)]
+    return [(lo, min(lo + MAX_BATCH, batch)) for lo in range(0, batch, MAX_BATCH)]
+
+
+def _merge_stats(acc, st):
+    """Statistics of a call that was cut into several C-ABI calls: counters and times add up."""
+    if acc is None:
+        return dict(st)
+    for k in ("sweeps_launched", "kernel_launches", "cell_updates", "solve_ms", "h2d_ms", "d2h_ms", "h2d_bytes",
+              "d2h_bytes", "dom_ms", "dom_launches"):
+        acc[k] += st[k]
+    return acc
+
+
+def _sync_torch_stream(device_array):
+    """Device operands: the library works on the ctx's own (non-blocking) stream, which is not ordered
+    against torch's current stream -- wait for whatever produced the tensors (S.copy_, computed
+    coefficients ...) before the library reads them.  (The call itself returns synchronised.)"""
+    import torch
+    torch.cuda.current_stream(device_array.device).synchronize()
+
+
+def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, profile=False, S_dev=None):
     L = _lib.load()
     ctx = ctx or _lib.default_context()
     opts = _lib.make_opts(ordering=ordering, mem_space=_lib.MEM_DEVICE if ops.device else _lib.MEM_HOST,
                           engine=engine, check_every=check_every, coef_strides=ops.strides,
                           profile=profile)
     fl = _flags_array(flags, ops.batch)
-    ptr_args = [C.c_void_p(ops.S_ptr)] + [C.c_void_p(p) if p is not None else None for p in ops.ptrs]
     fn = {"std2d": L.xinv_std2d, "gen2d": L.xinv_gen2d, "std3d": L.xinv_std3d}[kind]
-    rc = fn(ctx.handle, *ptr_args, *fn_args_tail(fl), C.byref(opts))
-    _lib.check(rc)
+    if ops.device and S_dev is not None:
+        _sync_torch_stream(S_dev)
+    stats = None
+    with ctx.lock:
+        for lo, hi in _batch_chunks(ops.batch):
+            off = lambda p, stride: C.c_void_p(p + 8 * lo * stride) if p is not None else None
+            ptr_args = [off(ops.S_ptr, ops.N)] + [off(p, st) for p, st in zip(ops.ptrs, ops.strides)]
+            flc = fl[lo:hi]                          # contiguous rows of the flags array
+            rc = fn(ctx.handle, *ptr_args, *fn_args_tail(flc, hi - lo), C.byref(opts))
+            _lib.check(rc)
+            stats = _merge_stats(stats, ctx.stats())
     ops.finish()
-    return fl, ctx.stats()
+    return fl, stats
 
 
 def solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg,
@@ -144,10 +181,10 @@ def solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, opt
     B = _zero_to_none(B)
     ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("F", F)], 2)
     ny, nx = ops.core
-    tail = lambda fl: (ops.batch, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
-                       float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
-                       C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
-    return _run("std2d", ops, tail, flags, ordering, engine, check_every, ctx, profile)
+    tail = lambda fl, nb: (nb, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
+                           float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
+                           C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("std2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S)
 
 
 def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_undef, BCy, BCx,
@@ -196,13 +233,19 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
             raise ValueError(f"{name} must have shape ({ny},)")
     opts = _lib.make_opts(mem_space=_lib.MEM_DEVICE if device else _lib.MEM_HOST, check_every=check_every)
     fl = _flags_array(flags, batch)
-    rc = L.xinv_std2d_rows(ctx.handle, S_ptr, ptr(rows[0]), ptr(rows[1]), F_ptr, ptr(rows[2]),
-                           float(user_undef), float(out_undef), batch, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
-                           float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
-                           C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance), C.byref(opts))
+    stats = None
+    with ctx.lock:
+        for lo, hi in _batch_chunks(batch):
+            off = lambda p: C.c_void_p(p.value + 8 * lo * ny * nx)
+            rc = L.xinv_std2d_rows(ctx.handle, off(S_ptr), ptr(rows[0]), ptr(rows[1]), off(F_ptr), ptr(rows[2]),
+                                   float(user_undef), float(out_undef), hi - lo, ny, nx, _lib.BC_CODES[BCy],
+                                   _lib.BC_CODES[BCx], float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg),
+                                   float(undef), C.c_void_p(fl[lo:hi].ctypes.data), int(mxLoop), float(tolerance),
+                                   C.byref(opts))
+            _lib.check(rc)
+            stats = _merge_stats(stats, ctx.stats())
     del keep
-    _lib.check(rc)
-    return S, fl, ctx.stats()
+    return S, fl, stats
 
 
 def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_undef, BCy, BCx, delx, delxSqr, ratio,
@@ -227,13 +270,19 @@ def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_unde
     S = _lib.pinned_empty(shape)
     opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
     fl = _flags_array(flags, batch)
-    rc = L.xinv_gen2d_rows(ctx.handle, C.c_void_p(S.ctypes.data), C.c_void_p(rows.ctypes.data), C.c_void_p(Gh.ctypes.data),
-                           int(g_mode), float(g_p1), float(g_p2), float(user_undef), float(out_undef), batch, ny, nx,
-                           _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delx), float(delxSqr), float(ratio),
-                           float(ratioQtr), float(ratioSqr), float(optArg), float(undef), C.c_void_p(fl.ctypes.data),
-                           int(mxLoop), float(tolerance), C.byref(opts))
-    _lib.check(rc)
-    return S, fl, ctx.stats()
+    stats = None
+    with ctx.lock:
+        for lo, hi in _batch_chunks(batch):
+            o = 8 * lo * ny * nx
+            rc = L.xinv_gen2d_rows(ctx.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
+                                   C.c_void_p(Gh.ctypes.data + o), int(g_mode), float(g_p1), float(g_p2),
+                                   float(user_undef), float(out_undef), hi - lo, ny, nx, _lib.BC_CODES[BCy],
+                                   _lib.BC_CODES[BCx], float(delx), float(delxSqr), float(ratio), float(ratioQtr),
+                                   float(ratioSqr), float(optArg), float(undef), C.c_void_p(fl[lo:hi].ctypes.data),
+                                   int(mxLoop), float(tolerance), C.byref(opts))
+            _lib.check(rc)
+            stats = _merge_stats(stats, ctx.stats())
+    return S, fl, stats
 
 
 def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ratioQtr,
@@ -243,10 +292,10 @@ def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ra
     B = _zero_to_none(B)
     ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("D", D), ("E", E), ("F", F), ("G", G)], 2)
     ny, nx = ops.core
-    tail = lambda fl: (ops.batch, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
-                       float(delx), float(delxSqr), float(ratio), float(ratioQtr), float(ratioSqr),
-                       float(optArg), float(undef), C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
-    return _run("gen2d", ops, tail, flags, ordering, engine, check_every, ctx, profile)
+    tail = lambda fl, nb: (nb, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
+                           float(delx), float(delxSqr), float(ratio), float(ratioQtr), float(ratioSqr),
+                           float(optArg), float(undef), C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("gen2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S)
 
 
 def solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1Sqr, optArg,
@@ -255,10 +304,10 @@ def solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1S
     """Batched ``invert_standard_3D`` (numbas.py:15-212) over S[..., nz, ny, nx], in place."""
     ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("F", F)], 3)
     nz, ny, nx = ops.core
-    tail = lambda fl: (ops.batch, nz, ny, nx, _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
-                       float(delxSqr), float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
-                       C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
-    return _run("std3d", ops, tail, flags, ordering, engine, check_every, ctx, profile)
+    tail = lambda fl, nb: (nb, nz, ny, nx, _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
+                           float(delxSqr), float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
+                           C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("std3d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S)
 
 
 # ---------------------------------------------------------------------------
