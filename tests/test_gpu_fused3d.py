@@ -1,0 +1,131 @@
+"""GPU parity of the plane-marching fused engine for invert_standard_3D (xinv_march3d.cuh: one
+red+black iteration, the y-extend rows, the norm and the loop control per pass) against the
+ordering-matched C oracle: BIT-EXACT fields, identical loop counts.
+
+XINV_FUSED3_VARIANT picks the instantiation (tile height, ring depth: X3_VARIANTS)."""
+import numpy as np
+import pytest
+
+import oracle
+import xinvert_b200 as xb
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+BCS = [("fixed", "fixed"), ("fixed", "periodic"), ("extend", "fixed"), ("extend", "periodic")]
+SHAPES = [(3, 3, 4), (5, 9, 12), (4, 13, 60), (7, 12, 64), (6, 29, 61), (9, 40, 122), (5, 57, 130), (12, 25, 258)]
+VARIANTS = ["0", "1", "2", "3", "4"]
+
+
+def _check(c, bcy, bcx, mx, tol=-1.0, omega=None, engine="fused", expect="fused"):
+    S_o, f_o = cases.run_std3d(oracle, c, bcy, bcx, mx, tol, omega=omega, ordering="colour")
+    S_g, f_g = cases.run_std3d(xb, c, bcy, bcx, mx, tol, omega=omega, engine=engine)
+    st = xb.default_context().stats()
+    assert st["engine"] == expect
+    assert np.array_equal(S_g, S_o), f"max diff {np.abs(S_g - S_o).max()} at {np.argwhere(S_g != S_o)[:5]}"
+    assert f_g[0] == f_o[0] and f_g[2] == f_o[2]
+    assert np.isclose(f_g[1], f_o[1], rtol=1e-6, atol=1e-13)    # a difference of two norms: tree sum vs serial sum
+    return st
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("bcy,bcx", BCS)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_fused3d_bit_exact(gpu_ctx, monkeypatch, variant, bcy, bcx, shape):
+    monkeypatch.setenv("XINV_FUSED3_VARIANT", variant)
+    if bcx == "periodic" and shape[2] % 2:
+        pytest.skip("odd nx + periodic-x uses the wrap-fix colours (colour engine)")
+    c = cases.random_std3d(*shape, seed=shape[0] * 10000 + shape[1] * 100 + shape[2])
+    for mx in (0, 1, 4):
+        _check(c, bcy, bcx, mx)
+
+
+@pytest.mark.parametrize("bcy,bcx", BCS)
+def test_fused3d_auto_variant_and_tolerance(gpu_ctx, bcy, bcx):
+    """Default variant choice, solved to tolerance: identical loop counts."""
+    c = cases.random_std3d(10, 44, 72, seed=11, land=0.05)
+    st = _check(c, bcy, bcx, 400, tol=1e-7, engine="auto")
+    assert st["sweeps_launched"] >= 1
+
+
+def test_fused3d_odd_nx_periodic_falls_back_to_colour_engine(gpu_ctx):
+    c = cases.random_std3d(6, 20, 31, seed=5)
+    _check(c, "fixed", "periodic", 5, engine="auto", expect="colour")
+    with pytest.raises(xb.XinvError) as ei:
+        cases.run_std3d(xb, c, "fixed", "periodic", 5, -1.0, engine="fused")
+    assert ei.value.code == -5
+
+
+def test_fused3d_undef_psi_and_undef_coefficients(gpu_ctx):
+    """undef values inside psi (not counted by the norm, not copied by y-extend) and inside A/B/C."""
+    c = cases.random_std3d(8, 30, 64, seed=21)
+    rng = np.random.default_rng(3)
+    for k in ("A", "B", "C"):
+        c[k][rng.random(c[k].shape) < 0.03] = cases.UNDEF
+    c["S0"][rng.random(c["S0"].shape) < 0.05] = cases.UNDEF
+    c["S0"][:, 1, 5:9] = cases.UNDEF          # rows that y-extend must not copy
+    c["S0"][:, -2, 20:30] = cases.UNDEF
+    for bcy, bcx in BCS:
+        _check(c, bcy, bcx, 3)
+
+
+def test_fused3d_batched_shared_coefficients_and_freezing(gpu_ctx):
+    """A batch of volumes sharing A, B, C (stride 0), each stopping on its own test."""
+    nb, shape = 5, (7, 26, 64)
+    c = cases.random_std3d(*shape, seed=8, land=0.05)
+    rng = np.random.default_rng(9)
+    F = np.stack([c["F"] * (1.0 + 3.0 * t) for t in range(nb)])
+    F[:, c["F"] == cases.UNDEF] = cases.UNDEF
+    S0 = rng.standard_normal((nb,) + shape) * np.array([1.0, 1e-3, 10.0, 1e-6, 1.0])[:, None, None, None]
+    p = c["p"]
+    S = S0.copy()
+    fl, st = xb.solve_standard_3D(S, c["A"], c["B"], c["C"], F, "fixed", "extend", "periodic", p["del1Sqr"],
+                                  p["ratio2Sqr"], p["ratio1Sqr"], p["optArg"], cases.UNDEF, mxLoop=300, tolerance=1e-6)
+    assert st["engine"] == "fused"
+    loops = set()
+    for t in range(nb):
+        ct = dict(c, F=np.ascontiguousarray(F[t]), S0=S0[t])
+        S_o, f_o = cases.run_std3d(oracle, ct, "extend", "periodic", 300, 1e-6, ordering="colour")
+        assert np.array_equal(S[t], S_o), t
+        assert fl[t, 2] == f_o[2] and fl[t, 0] == f_o[0]
+        loops.add(int(f_o[2]))
+    assert len(loops) > 1, "slices were meant to stop at different iterations"
+
+
+def test_fused3d_batched_dense_coefficients(gpu_ctx):
+    nb, shape = 3, (5, 20, 70)
+    c = cases.random_std3d(*shape, seed=31, batch=nb)
+    p = c["p"]
+    S = c["S0"].copy()
+    fl, st = xb.solve_standard_3D(S, c["A"], c["B"], c["C"], c["F"], "fixed", "fixed", "fixed", p["del1Sqr"],
+                                  p["ratio2Sqr"], p["ratio1Sqr"], p["optArg"], cases.UNDEF, mxLoop=6, tolerance=-1.0)
+    assert st["engine"] == "fused"
+    for t in range(nb):
+        ct = dict(A=c["A"][t], B=c["B"][t], C=c["C"][t], F=c["F"][t], S0=c["S0"][t], p=p)
+        S_o, f_o = cases.run_std3d(oracle, ct, "fixed", "fixed", 6, -1.0, ordering="colour")
+        assert np.array_equal(S[t], S_o), t
+
+
+def test_fused3d_warm_start_equals_one_long_solve(gpu_ctx):
+    """S is in/out: two solves of 3 sweeps continue where one of 6 would be (animate_iteration's contract)."""
+    c = cases.random_std3d(6, 30, 64, seed=14)
+    S6, _ = cases.run_std3d(xb, c, "extend", "periodic", 5, -1.0, engine="fused")
+    S3, _ = cases.run_std3d(xb, c, "extend", "periodic", 2, -1.0, engine="fused")
+    c2 = dict(c, S0=S3)
+    S33, _ = cases.run_std3d(xb, c2, "extend", "periodic", 2, -1.0, engine="fused")
+    assert np.array_equal(S6, S33)
+
+
+def test_fused3d_overflow_flag(gpu_ctx):
+    """A diverging iteration (omega far above 2) sets flags[0] exactly when the oracle does."""
+    c = cases.random_std3d(6, 20, 64, seed=17, land=0.0)
+    _check(c, "fixed", "periodic", 2000, tol=1e-30, omega=2.9)
+
+
+def test_fused3d_equals_colour_engine_at_c3_size(gpu_ctx):
+    """37 x 180 x 360 (BASELINE configs[2]): fused and colour engines give the same bits."""
+    c = cases.random_std3d(37, 180, 360, seed=3, land=0.1)
+    S_f, f_f = cases.run_std3d(xb, c, "extend", "periodic", 9, -1.0, engine="fused")
+    S_c, f_c = cases.run_std3d(xb, c, "extend", "periodic", 9, -1.0, engine="colour")
+    assert np.array_equal(S_f, S_c)
+    assert f_f[2] == f_c[2]

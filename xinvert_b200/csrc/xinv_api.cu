@@ -22,6 +22,7 @@
 #include "xinv_device.cuh"
 #include "xinv_colour_engine.cuh"
 #include "xinv_march2d.cuh"
+#include "xinv_march3d.cuh"
 #include "xinv_lex_engine.cuh"
 
 // ---------------------------------------------------------------------------
@@ -77,6 +78,7 @@ struct Problem {
     int nblk_norm = 0;
     int h_nactive = 0;
     FusedPlan fused{};
+    Fused3Plan fused3{};         // 3-D standard form (xinv_march3d.cuh)
     bool front = false;          // xinv_std2d_rows: S is output only, de-masked on the device
 };
 
@@ -181,6 +183,7 @@ extern "C" void xinv_destroy(xinv_ctx *c)
     release(c->state); release(c->psum); release(c->pcnt); release(c->ticket); release(c->nactive); release(c->flags_in);
     release(c->nccl_buf);
     fused_plan_release(c->pb.fused);
+    fused3_plan_release(c->pb.fused3);
     xm_work_release(c->xm_work);
     if (c->h_nactive_pinned) cudaFreeHost(c->h_nactive_pinned);
     for (auto e : c->prof_ev) cudaEventDestroy(e);
@@ -345,6 +348,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     CK(cudaSetDevice(c->device));
     Problem &pb = c->pb;
     fused_plan_release(pb.fused);
+    fused3_plan_release(pb.fused3);
     pb = Problem();
     pb.kind = a.kind;
     pb.batch = a.batch;
@@ -493,7 +497,15 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     pb.engine = XINV_ENGINE_COLOUR;
     if (pb.ordering == XINV_ORDER_COLOUR && o.engine != XINV_ENGINE_COLOUR) {
         std::string why;
-        if (fused_plan_supported(pb.kind, pb.hasB, g, why)) {
+        if (pb.kind == XD_STD3D) {
+            const char *e3 = getenv("XINV_FUSED3");
+            if (e3 && atoi(e3) == 0) why = "disabled by XINV_FUSED3=0";
+            else if (fused3_plan_supported(g, why) &&
+                     fused3_plan_build(pb.fused3, c->xm_work, c->sm_count, g, pb.q, pb.batch, pb.dS, c->stream, why) == 0)
+                pb.engine = XINV_ENGINE_FUSED;
+            if (pb.engine != XINV_ENGINE_FUSED && o.engine == XINV_ENGINE_FUSED)
+                return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
+        } else if (fused_plan_supported(pb.kind, pb.hasB, g, why)) {
             rc = fused_plan_build(pb.fused, c->xm_work, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, pb.mxLoop, c->stream, why,
                                   a.front ? &front : nullptr);
             if (rc == 0) pb.engine = XINV_ENGINE_FUSED;
@@ -506,6 +518,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     {
         int np = pb.nblk_norm;
         if (pb.engine == XINV_ENGINE_FUSED && pb.fused.nblk_partials > np) np = pb.fused.nblk_partials;
+        if (pb.engine == XINV_ENGINE_FUSED && pb.fused3.nblk_partials > np) np = pb.fused3.nblk_partials;
         if ((rc = ensure(c->psum, sizeof(double) * a.batch * np))) return rc;
         if ((rc = ensure(c->pcnt, sizeof(i64) * a.batch * np))) return rc;
     }
@@ -520,7 +533,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     CK(cudaMemsetAsync(c->ticket.p, 0, sizeof(unsigned) * a.batch, c->stream));
     {
         // iterations of the first pass: T, but never more sweeps than mxLoop allows (loop = 0 .. mxLoop)
-        const int nit0 = (pb.engine == XINV_ENGINE_FUSED) ? (int)((a.mxLoop + 1 < (i64)pb.fused.T) ? a.mxLoop + 1 : (i64)pb.fused.T) : 1;
+        const int nit0 = (pb.engine == XINV_ENGINE_FUSED && pb.fused.built) ? (int)((a.mxLoop + 1 < (i64)pb.fused.T) ? a.mxLoop + 1 : (i64)pb.fused.T) : 1;
         xd_init_state_kernel<<<(unsigned)((a.batch + 127) / 128), 128, 0, c->stream>>>(
             (XdSliceState *)c->state.p, (const double *)ftmp.p, (int)a.batch, (int *)c->nactive.p, nit0);
     }
@@ -537,8 +550,8 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     pb.h_nactive = (int)a.batch;
 
     c->stats.engine = pb.engine;
-    c->stats.iters_per_pass = (pb.engine == XINV_ENGINE_FUSED) ? pb.fused.T : 1;
-    c->stats.row_coeffs = (pb.engine == XINV_ENGINE_FUSED && pb.fused.rc) ? 1 : 0;
+    c->stats.iters_per_pass = (pb.engine == XINV_ENGINE_FUSED && pb.fused.built) ? pb.fused.T : 1;
+    c->stats.row_coeffs = (pb.engine == XINV_ENGINE_FUSED && pb.fused.built && pb.fused.rc) ? 1 : 0;
     pb.open = true;
     return XINV_OK;
 }
@@ -640,7 +653,8 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
     if (pb.batch == 0 || pb.h_nactive == 0) { if (n_active_out) *n_active_out = 0; return XINV_OK; }
     // a pass (launch) performs >= 1 sweep on every active slice, except for at most one
     // "redo" pass per slice (fused engine, T > 1): at most mxLoop + 2 passes (numbas.py:410)
-    const i64 max_passes = pb.mxLoop + 1 + ((pb.engine == XINV_ENGINE_FUSED && pb.fused.T > 1) ? 1 : 0);
+    const bool f3 = (pb.engine == XINV_ENGINE_FUSED && pb.fused3.built);
+    const i64 max_passes = pb.mxLoop + 1 + ((pb.engine == XINV_ENGINE_FUSED && !f3 && pb.fused.T > 1) ? 1 : 0);
     const i64 remaining = max_passes - pb.sweeps_launched;
     if (sweeps <= 0) sweeps = auto_check_every(c, pb);
     if (sweeps > remaining) sweeps = remaining;
@@ -652,7 +666,13 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
             rc = lex_sweep(c->stream, pb.kind, pb.hasB, pb.g, pb.q, pb.batch, pb.dS, (XdSliceState *)c->state.p,
                            pb.nblk_norm, (double *)c->psum.p, (i64 *)c->pcnt.p, (unsigned *)c->ticket.p,
                            (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
-        else if (pb.engine == XINV_ENGINE_FUSED) {
+        else if (f3) {
+            did = sweeps - it < pb.fused3.ppl ? sweeps - it : pb.fused3.ppl;     // passes in this launch
+            rc = fused3_sweep(pb.fused3, c->stream, (XdSliceState *)c->state.p, (double *)c->psum.p, (i64 *)c->pcnt.p,
+                              (unsigned *)c->ticket.p, (int *)c->nactive.p, pb.tol, pb.mxLoop, (int)did,
+                              &c->stats.kernel_launches);
+            if (rc) return set_err(XINV_E_CUDA, "3-D fused engine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else if (pb.engine == XINV_ENGINE_FUSED) {
             did = sweeps - it < pb.fused.ppl ? sweeps - it : pb.fused.ppl;       // passes in this launch
             rc = fused_sweep(pb.fused, c->stream, (XdSliceState *)c->state.p, (double *)c->psum.p, (i64 *)c->pcnt.p,
                              (unsigned *)c->ticket.p, (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, (int)did,
@@ -698,7 +718,11 @@ extern "C" int xinv_end(xinv_ctx *c)
     pb.open = false;
     if (pb.batch == 0) return XINV_OK;
     const XdGeom &g = pb.g;
-    if (pb.engine == XINV_ENGINE_FUSED) {
+    if (pb.engine == XINV_ENGINE_FUSED && pb.fused3.built) {
+        fused3_unpack(pb.fused3, pb.dS, (const XdSliceState *)c->state.p, c->stream);
+        c->stats.kernel_launches++;
+        CK(cudaGetLastError());
+    } else if (pb.engine == XINV_ENGINE_FUSED) {
         fused_unpack(pb.fused, pb.dS, (const XdSliceState *)c->state.p, c->stream);
         c->stats.kernel_launches++;
         CK(cudaGetLastError());
@@ -726,12 +750,15 @@ extern "C" int xinv_end(xinv_ctx *c)
     }
     c->stats.cell_updates = updates;
     c->stats.sweep_ms = max_done ? c->stats.solve_ms / (double)max_done : 0.0;
-    if (pb.profile && pb.engine == XINV_ENGINE_FUSED && pb.ordering != XINV_ORDER_LEX && pb.fused.T > 0) {
+    if (pb.profile && pb.engine == XINV_ENGINE_FUSED && pb.ordering != XINV_ORDER_LEX && pb.fused3.built) {
+        c->stats.dom_launches = max_done;
+    } else if (pb.profile && pb.engine == XINV_ENGINE_FUSED && pb.ordering != XINV_ORDER_LEX && pb.fused.T > 0) {
         // passes that did work: the chunks were timed as a whole and may end with passes that found every
         // slice stopped (a few microseconds each, left in dom_ms); count only the real ones
         c->stats.dom_launches = (max_done + pb.fused.T - 1) / pb.fused.T;
     }
     fused_plan_release(pb.fused);
+    fused3_plan_release(pb.fused3);
     return XINV_OK;
 }
 
