@@ -2,7 +2,8 @@
 red+black iteration, the y-extend rows, the norm and the loop control per pass) against the
 ordering-matched C oracle: BIT-EXACT fields, identical loop counts.
 
-XINV_FUSED3_VARIANT picks the instantiation (tile height, ring depth: X3_VARIANTS)."""
+XINV_FUSED3_VARIANT picks the tile height (X3_VARIANTS); the AROW kernels are chosen automatically when A is
+constant along x (invert_omega's A = f^2 cos(lat)); XINV_FUSED3_AROW=0 forces the general kernels."""
 import numpy as np
 import pytest
 
@@ -14,30 +15,66 @@ pytestmark = pytest.mark.gpu
 
 BCS = [("fixed", "fixed"), ("fixed", "periodic"), ("extend", "fixed"), ("extend", "periodic")]
 SHAPES = [(3, 3, 4), (5, 9, 12), (4, 13, 60), (7, 12, 64), (6, 29, 61), (9, 40, 122), (5, 57, 130), (12, 25, 258)]
-VARIANTS = ["0", "1", "2", "3", "4"]
+VARIANTS = ["0", "1", "2", "3", "4", "5"]      # xinv_march3d.cuh: X3_VARIANTS (tile height, ring depth, CTAs per SM)
 
 
-def _check(c, bcy, bcx, mx, tol=-1.0, omega=None, engine="fused", expect="fused"):
+def _arow(c):
+    """The same problem with A constant along x (a different value per level and row)."""
+    A = np.ascontiguousarray(np.broadcast_to(c["A"][..., :1], c["A"].shape))
+    return dict(c, A=A)
+
+
+def _check(c, bcy, bcx, mx, tol=-1.0, omega=None, engine="fused", expect="fused", arow=None):
     S_o, f_o = cases.run_std3d(oracle, c, bcy, bcx, mx, tol, omega=omega, ordering="colour")
     S_g, f_g = cases.run_std3d(xb, c, bcy, bcx, mx, tol, omega=omega, engine=engine)
     st = xb.default_context().stats()
     assert st["engine"] == expect
+    if arow is not None:
+        assert st["row_coeffs"] == int(arow)
     assert np.array_equal(S_g, S_o), f"max diff {np.abs(S_g - S_o).max()} at {np.argwhere(S_g != S_o)[:5]}"
     assert f_g[0] == f_o[0] and f_g[2] == f_o[2]
     assert np.isclose(f_g[1], f_o[1], rtol=1e-6, atol=1e-13)    # a difference of two norms: tree sum vs serial sum
     return st
 
 
+@pytest.mark.parametrize("arow", [False, True])
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("bcy,bcx", BCS)
 @pytest.mark.parametrize("shape", SHAPES)
-def test_fused3d_bit_exact(gpu_ctx, monkeypatch, variant, bcy, bcx, shape):
+def test_fused3d_bit_exact(gpu_ctx, monkeypatch, arow, variant, bcy, bcx, shape):
     monkeypatch.setenv("XINV_FUSED3_VARIANT", variant)
     if bcx == "periodic" and shape[2] % 2:
         pytest.skip("odd nx + periodic-x uses the wrap-fix colours (colour engine)")
     c = cases.random_std3d(*shape, seed=shape[0] * 10000 + shape[1] * 100 + shape[2])
+    if arow:
+        c = _arow(c)
     for mx in (0, 1, 4):
-        _check(c, bcy, bcx, mx)
+        _check(c, bcy, bcx, mx, arow=arow)
+
+
+@pytest.mark.parametrize("arow", [False, True])
+@pytest.mark.parametrize("variant", ["0", "2", "3"])
+@pytest.mark.parametrize("ntz", ["2", "3", "5"])
+@pytest.mark.parametrize("bcy,bcx", BCS)
+def test_fused3d_level_ranges_split_over_tiles(gpu_ctx, monkeypatch, arow, variant, ntz, bcy, bcx):
+    """Small volumes split the levels over several tiles (2 halo levels each): every range boundary inside the grid."""
+    monkeypatch.setenv("XINV_FUSED3_VARIANT", variant)
+    monkeypatch.setenv("XINV_FUSED3_NTZ", ntz)
+    for shape in ((11, 21, 64), (26, 14, 70)):
+        c = cases.random_std3d(*shape, seed=shape[0] + int(ntz))
+        if arow:
+            c = _arow(c)
+        for mx in (0, 3):
+            _check(c, bcy, bcx, mx, arow=arow)
+
+
+def test_fused3d_arow_equals_general_kernels(gpu_ctx, monkeypatch):
+    """The same x-constant A through the general kernels (XINV_FUSED3_AROW=0)."""
+    c = _arow(cases.random_std3d(9, 40, 122, seed=77))
+    c["A"][3, 7, :] = cases.UNDEF              # a whole row of undef A
+    _check(c, "extend", "periodic", 5, arow=True)
+    monkeypatch.setenv("XINV_FUSED3_AROW", "0")
+    _check(c, "extend", "periodic", 5, arow=False)
 
 
 @pytest.mark.parametrize("bcy,bcx", BCS)
@@ -72,7 +109,7 @@ def test_fused3d_undef_psi_and_undef_coefficients(gpu_ctx):
 def test_fused3d_batched_shared_coefficients_and_freezing(gpu_ctx):
     """A batch of volumes sharing A, B, C (stride 0), each stopping on its own test."""
     nb, shape = 5, (7, 26, 64)
-    c = cases.random_std3d(*shape, seed=8, land=0.05)
+    c = _arow(cases.random_std3d(*shape, seed=8, land=0.05))
     rng = np.random.default_rng(9)
     F = np.stack([c["F"] * (1.0 + 3.0 * t) for t in range(nb)])
     F[:, c["F"] == cases.UNDEF] = cases.UNDEF

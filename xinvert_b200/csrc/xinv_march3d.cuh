@@ -2,9 +2,9 @@
 // numbas.py:15-212): ONE pass over the volume performs a complete red+black SOR
 // iteration, the y-"extend" rows, sum|omega| / count and the loop control.
 //
-// Design ("plane marching"): a CTA owns a column of tiles -- TJ rows x 64 columns of
-// every level -- and marches along z.  One warp per tile row, one column pair per lane
-// (as in the 2-D engine: x-neighbours by warp shuffle).
+// Design ("plane marching"): a CTA owns a tile of TJ rows x 64 columns x a range of levels
+// and marches along z.  One warp per tile row, one column pair per lane (as in the 2-D
+// engine: x-neighbours by warp shuffle).
 //   * Once per solve the engine builds padded copies of the operands (same layout as the
 //     2-D engine: XM_PADL ghost columns left, >= XM_GHOST right, holding the periodic
 //     wrap-around neighbours) and two derived arrays, with the reference's own operations:
@@ -12,23 +12,36 @@
 //              level / row / fixed column, an undef operand: numbas.py:117-118, :147-150)
 //        fac = optArg / ((A[k+1]+A[k])*ratio2Sqr + (B[j+1]+B[j])*ratio1Sqr + (C[i+1]+C[i]))
 //                                                                     (numbas.py:166-168)
-//   * Thread 0 feeds a K-stage shared-memory ring with TMA box loads: per level one box of
-//     omega, A, C, Fd, fac (TJ x 64) and B (TJ+1 x 64: the row north of the tile too),
-//     completion on one mbarrier per stage, K-1 levels ahead of the consumers.
-//   * z-neighbours live in registers (the lane keeps its column pair of the last three
-//     levels and A of the last two); y-neighbours of the red half step are read from the
+//     (forming the factor in the kernel instead was measured: 31 -> 44 us per sweep on the
+//     37 x 180 x 360 case -- the march is bound by dependent latency, not by bytes.)
+//   * AROW kernels: A constant along x (detected on the device; invert_omega's A = f^2 cos(lat),
+//     apps.py:2025-2036) arrives as one value per row instead of a 64-column tile.
+//   * Warp 0 is the producer: it feeds a K-stage shared-memory ring with TMA box loads, per level
+//     one box of omega (TJ rows x 64 columns), B (TJ-1 rows: the updated rows and the row north of
+//     them) and A, C, Fd, fac (the TJ-2 rows on which anything is ever updated); a "landed"
+//     mbarrier per stage completes on the TMA byte count, a "free" mbarrier per stage collects one
+//     arrival per compute warp, so the producer runs up to K levels ahead and the issue of the
+//     loads is off the critical path of the march.  (Rows 0 and TJ-1 of a tile are never updated and
+//     their warps would compute nothing anyone reads: warp 0 produces, warp TJ-1 is spare, the TJ-2
+//     compute warps meet at a named barrier.)
+//   * z-neighbours live in registers (the lane keeps its column pair of the last four
+//     levels and A of the last three); y-neighbours of the red half step are read from the
 //     staged (still untouched) level, those of the black half step from a small exchange
 //     buffer into which every warp publishes its row after the red half step.
-//   * Schedule per step s (level s has just arrived): red cells of level s-1 (colour 0 =
-//     (i+j+k) even, as the colour engine and the oracle), black cells of level s-2, which
+//   * Schedule per step (level kl has just arrived): red cells of level kl-1 (colour 0 =
+//     (i+j+k) even, as the colour engine and the oracle), black cells of level kl-2, which
 //     is then complete: norm accumulation, store to the OTHER omega buffer (ping-pong:
-//     neighbouring tiles still need the old values).  One __syncthreads per step.
-//   * A tile has a 2-cell halo in y and x (red results of the halo are recomputed; black
-//     results only exist for the owned TJ-4 rows x 60 columns) and none in z.
+//     neighbouring tiles still need the old values).  One __syncthreads per step.  The march is
+//     unrolled four steps deep, so the colour of the lane's even column and every slot of the
+//     register windows are compile-time constants: no register is ever moved.
+//   * A tile has a 2-cell halo in y and x and -- when the levels are split over several tiles
+//     to fill the machine (small volumes) -- 2 levels in z: red results of the halo are
+//     recomputed, black results only exist for the owned TJ-4 rows x 60 columns x levels.
 //   * Per-tile (sum, count) partials are combined in fixed order by the CTA that finishes
 //     a slice last (atomic ticket), which then runs numbas.py:197-210.
 // HBM/L2 traffic per pass (= per iteration): omega r+w, A, B, C, Fd, fac = 56 N bytes
-// (x the halo overhead of the tiling), of which 48 N are algorithmic (omega r+w, A, B, C, F).
+// (AROW: 48 N), x the halo overhead of the tiling on the reads; 48 N (40 N) are algorithmic
+// (omega r+w, A, B, C, F).
 #pragma once
 #include "xinv_march2d.cuh"
 
@@ -38,13 +51,13 @@ struct X3Args {
     double *Sbuf[2];          // padded omega buffers [batch][nz][ny][pitch]
     i64 pitch, plane, slice;  // plane = ny * pitch, slice = nz * plane
     int nz, ny, nx;
-    int ntx, nty, RB;         // column tiles, row tiles, owned rows per tile (TJ - 4)
+    int ntx, nty, ntz, RB, ZB;   // column / row / level tiles; owned rows (TJ - 4) and levels (even) per tile
     int batch;
     int bcy, bcx;
     int cbA, cbB, cbC, cbFd, cbFac;   // 1: the array has a batch axis, 0: one volume shared by the batch
     double r2, r1, undef;     // ratio2Sqr, ratio1Sqr
     XdSliceState *st;
-    double *psum;             // [batch][ntx*nty]
+    double *psum;             // [batch][ntx*nty*ntz]
     i64 *pcnt;
     unsigned *ticket;
     int *nactive;
@@ -71,32 +84,219 @@ __device__ __forceinline__ double x3_cell(double Sc, double Su, double Sd, doubl
 
 __device__ __forceinline__ double2 x3_ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 
-template <int TJ, int K>
-__global__ void __launch_bounds__(TJ * 32, 1)
+// Shared-memory layout of one ring stage (offsets in doubles).  Row r of the omega box is global row
+// y0 - 2 + r; the A, C, Fd, fac and B boxes start one row later (row r <-> y0 - 1 + r).
+template <int TJ, bool AROW>
+struct X3Lay {
+    static constexpr int W = X3_W;
+    static constexpr int RC = TJ - 2;            // rows of A, C, Fd, fac: everything that is ever updated
+    static constexpr int RBN = TJ - 1;           // rows of B: those and the row north of them
+    static constexpr int OFF_S = 0;
+    static constexpr int OFF_A = TJ * W;
+    static constexpr int A_SZ = AROW ? 32 : RC * W;          // AROW: TJ values (rows y0-2 ...: TMA start coordinates must be even), padded to 128 bytes
+    static constexpr int OFF_C = OFF_A + A_SZ;
+    static constexpr int OFF_FD = OFF_C + RC * W;
+    static constexpr int OFF_FAC = OFF_FD + RC * W;
+    static constexpr int OFF_B = OFF_FAC + RC * W;
+    static constexpr int STAGE = OFF_B + RBN * W;
+    static constexpr uint32_t TX_BYTES = (uint32_t)((TJ * W + (AROW ? TJ : RC * W) + 3 * RC * W + RBN * W) * sizeof(double));
+    static_assert(TJ <= 32 && (TJ % 2) == 0, "row-value box: at most 256 bytes, a multiple of 16");
+};
+
+// Everything the march of one tile needs besides its registers.
+struct X3Tile {
+    const double *ringrow;   // ring + (this warp's row) * W + 2 * lane
+    const double *arow;      // AROW: ring + OFF_A + this warp's row
+    double *xrow;            // exchange buffers, same offset as ringrow
+    uint64_t *bars;          // [K] "level has landed" (TMA transaction barriers) | [K] "stage is free again" (compute warps arrive)
+    double *outp;            // output row of level kbase - 2 (advanced by one level per step)
+    i64 plane;
+    int nsteps;              // steps of the march; step s brings level kbase + s (kbase even)
+    int s_load;              // steps [0, s_load) bring a level
+    int s_red0, s_red1;      // steps in which red cells (of the level that arrived one step earlier) are updated
+    int s_blk0, s_blk1;      // ... black cells (two steps earlier): the owned, updatable levels
+    int s_fin0, s_fin1;      // steps in which an owned level is complete (norm)
+    int s_ext0, s_ext1;      // arrival steps of the levels 1 .. nz-2 (y-extend)
+    int nx, gx;
+    int wn, ws;              // smem offsets of the rows north / south of this warp's row
+    bool periodic, ext_j0, ext_jN, ext_j1, ext_jM;
+    bool own_x, own_y, ghe, ghw, edge;
+    double undef, r2, r1;
+};
+
+// ring position: carried from tile to tile (the mbarrier phases go on)
+struct X3Ring {
+    int cons;                // stage the next arriving / issued level sits in
+    unsigned phase;          // bit k: parity to wait for on stage k's barrier (compute warps: "landed"; producer: "free")
+};
+
+__device__ __forceinline__ void x3_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xf_smem_u32(bar)) : "memory");
+}
+// the compute warps of a CTA meet at named barrier 1 (the producer warp and the spare warp do not take part)
+__device__ __forceinline__ void x3_bar_compute(int nthreads)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// One tile.  JODD = parity of this warp's global row: with the step index known modulo 4 (4-step unrolled
+// loop, kbase even) the colour of the lane's even column is a compile-time constant and the register windows
+// (omega of the last four levels, A of the last three, the operands saved for the black half step) are
+// indexed by constants.
+template <int TJ, int K, bool AROW, bool JODD>
+__device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &nsum, int &ncnt)
+{
+    using L = X3Lay<TJ, AROW>;
+    constexpr int W = X3_W;
+    constexpr int TILE = TJ * W;
+    // the coefficient boxes start one row below the omega box: fold the -W into the offsets
+    constexpr int OFF_S = L::OFF_S, OFF_A = L::OFF_A - W, OFF_C = L::OFF_C - W, OFF_FD = L::OFF_FD - W, OFF_FAC = L::OFF_FAC - W;
+    constexpr int OFF_BC = L::OFF_B - W, OFF_BN = L::OFF_B;
+    constexpr int STAGE = L::STAGE;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    const double undef = t.undef, r2 = t.r2, r1 = t.r1;
+    double2 P[4] = {zero2, zero2, zero2, zero2};     // omega: the level of step s in P[s & 3]
+    double2 Aw[4] = {zero2, zero2, zero2, zero2};    // A:     likewise
+    // operands of the black cell of the level that arrived one step earlier, saved at step s in slot s & 1
+    double kBc[2] = {0.0, 0.0}, kBn[2] = {0.0, 0.0}, kCw[2] = {0.0, 0.0}, kCe[2] = {0.0, 0.0}, kFac[2] = {0.0, 0.0};
+    double kFd[2] = {xm_skip_value(), xm_skip_value()};
+    double *outp = t.outp;
+    int prev_off = 0;                                // stage offset (doubles) of the level that arrived in the previous step
+    int prev_stage = -1;                             // ... and its stage (-1: none to hand back)
+    const int lane = threadIdx.x & 31;
+
+    auto step = [&](auto u_tag, const int s) {
+        constexpr int U = decltype(u_tag)::value;    // s & 3
+        constexpr int U1 = (U + 3) & 3, U2 = (U + 2) & 3, U3 = (U + 1) & 3;   // slots of the levels of steps s-1, s-2, s-3
+        // red cell of the level of step s-1 = the even column of the pair  <=>  j + kbase + s - 1 even
+        constexpr bool RX = ((int(JODD) + U + 1) & 1) == 0;
+        int cur_off = prev_off, cur_stage = -1;
+        // ---- a level arrives ----
+        if (s < t.s_load) {
+            xf_mbar_wait(&t.bars[rg.cons], (rg.phase >> rg.cons) & 1u);
+            rg.phase ^= (1u << rg.cons);
+            cur_off = rg.cons * STAGE;
+            cur_stage = rg.cons;
+            rg.cons = (rg.cons + 1 == K) ? 0 : rg.cons + 1;
+            const double *g = t.ringrow + cur_off;
+            P[U] = x3_ld2(g + OFF_S);
+            if (AROW) { const double av = t.arow[cur_off]; Aw[U] = make_double2(av, av); }
+            else      Aw[U] = x3_ld2(g + OFF_A);
+            if ((t.ext_j0 | t.ext_jN) & (s >= t.s_ext0) & (s <= t.s_ext1)) {   // numbas.py:87-115: levels 1..nz-2 only
+                if (t.ext_j0) P[U] = xm_extend(P[U], x3_ld2(g + OFF_S + W), t.gx, t.nx, t.periodic, undef);
+                else          P[U] = xm_extend(P[U], x3_ld2(g + OFF_S - W), t.gx, t.nx, t.periodic, undef);
+            }
+        } else {
+            P[U] = zero2; Aw[U] = zero2;
+        }
+        // ---- red cells of the level of step s-1 (neighbours in y: the staged level, still untouched) ----
+        if ((s >= t.s_red0) & (s <= t.s_red1)) {
+            const double *r = t.ringrow + prev_off;
+            const double2 Bc = x3_ld2(r + OFF_BC), Bn = x3_ld2(r + OFF_BN), Cc = x3_ld2(r + OFF_C);
+            const double2 Fd = x3_ld2(r + OFF_FD), Fc = x3_ld2(r + OFF_FAC);
+            double2 Sn = x3_ld2(r + OFF_S + t.wn), Ss = x3_ld2(r + OFF_S + t.ws);
+            if (t.ext_j1 | t.ext_jM) {
+                // the extended boundary row as the cells of rows 1 / ny-2 see it: their own old value
+                if (t.ext_j1) { if (P[U1].x != undef) Ss.x = P[U1].x; if (P[U1].y != undef) Ss.y = P[U1].y; }
+                if (t.ext_jM) { if (P[U1].x != undef) Sn.x = P[U1].x; if (P[U1].y != undef) Sn.y = P[U1].y; }
+            }
+            const double Cnext = xm_shfl_down1(Cc.x);              // C of the column east of the pair
+            if (RX) {
+                const double nb = xm_shfl_up1(P[U1].y);
+                P[U1].x = x3_cell(P[U1].x, P[U].x, P[U2].x, Sn.x, Ss.x, P[U1].y, nb, Aw[U].x, Aw[U1].x, Bn.x, Bc.x, Cc.y, Cc.x,
+                                  Fd.x, Fc.x, r2, r1);
+                kBc[U & 1] = Bc.y; kBn[U & 1] = Bn.y; kCw[U & 1] = Cc.y; kCe[U & 1] = Cnext; kFd[U & 1] = Fd.y; kFac[U & 1] = Fc.y;
+            } else {
+                const double nb = xm_shfl_down1(P[U1].x);
+                P[U1].y = x3_cell(P[U1].y, P[U].y, P[U2].y, Sn.y, Ss.y, nb, P[U1].x, Aw[U].y, Aw[U1].y, Bn.y, Bc.y, Cnext, Cc.y,
+                                  Fd.y, Fc.y, r2, r1);
+                kBc[U & 1] = Bc.x; kBn[U & 1] = Bn.x; kCw[U & 1] = Cc.x; kCe[U & 1] = Cc.y; kFd[U & 1] = Fd.x; kFac[U & 1] = Fc.x;
+            }
+        } else {
+            kFd[U & 1] = xm_skip_value();
+        }
+        // publish the row (red cells final for this iteration) for the black half step of the next step
+        *reinterpret_cast<double2 *>(t.xrow + (U & 1) * TILE) = P[U1];
+        // ---- black cells of the level of step s-2 (neighbours in y: rows published in the previous step) ----
+        const bool blk = (s >= t.s_blk0) & (s <= t.s_blk1);
+        if (blk) {
+            constexpr int Q = (U + 1) & 1;                         // slot written in the previous step
+            const double *xr = t.xrow + Q * TILE;
+            const double2 Sn = x3_ld2(xr + t.wn), Ss = x3_ld2(xr + t.ws);
+            if (RX) {                                              // red of step s-1's level even column <=> black of step s-2's
+                const double nb = xm_shfl_up1(P[U2].y);
+                P[U2].x = x3_cell(P[U2].x, P[U1].x, P[U3].x, Sn.x, Ss.x, P[U2].y, nb, Aw[U1].x, Aw[U2].x, kBn[Q], kBc[Q], kCe[Q],
+                                  kCw[Q], kFd[Q], kFac[Q], r2, r1);
+            } else {
+                const double nb = xm_shfl_down1(P[U2].x);
+                P[U2].y = x3_cell(P[U2].y, P[U1].y, P[U3].y, Sn.y, Ss.y, nb, P[U2].x, Aw[U1].y, Aw[U2].y, kBn[Q], kBc[Q], kCe[Q],
+                                  kCw[Q], kFd[Q], kFac[Q], r2, r1);
+            }
+        }
+        // ---- an owned level is complete: norm over owned cells (numbas.py:1689-1708), store ----
+        if ((s >= t.s_fin0) & (s <= t.s_fin1)) {
+            xm_norm_acc_lane(nsum, ncnt, P[U2].x, t.own_x, undef);
+            xm_norm_acc_lane(nsum, ncnt, P[U2].y, t.own_y, undef);
+            if (blk) {                                             // levels 0 and nz-1 never change
+                xm_store2_if(t.own_y, outp, P[U2]);
+                if (t.edge) {                                      // odd nx / periodic ghost columns (warp-uniform)
+                    xm_store1_if(t.own_x & !t.own_y, outp, P[U2].x);
+                    xm_store2_if(t.ghe, outp + t.nx, P[U2]);
+                    xm_store2_if(t.ghw, outp - t.nx, P[U2]);
+                }
+            }
+        }
+        outp += t.plane;
+        // the stage of the previous step's level has been read for the last time: hand it back to the producer
+        if (prev_stage >= 0) {
+            __syncwarp();
+            if (lane == 0) x3_mbar_arrive(&t.bars[K + prev_stage]);
+        }
+        prev_off = cur_off;
+        prev_stage = cur_stage;
+        x3_bar_compute((TJ - 2) * 32);           // rows published
+    };
+
+    for (int s0 = 0; s0 < t.nsteps; s0 += 4) {
+        step(std::integral_constant<int, 0>{}, s0);
+        if (s0 + 1 < t.nsteps) step(std::integral_constant<int, 1>{}, s0 + 1);
+        if (s0 + 2 < t.nsteps) step(std::integral_constant<int, 2>{}, s0 + 2);
+        if (s0 + 3 < t.nsteps) step(std::integral_constant<int, 3>{}, s0 + 3);
+    }
+    if (prev_stage >= 0) {                           // a level that arrived in the very last step
+        __syncwarp();
+        if (lane == 0) x3_mbar_arrive(&t.bars[K + prev_stage]);
+    }
+}
+
+template <int TJ, int K, int MINB, bool AROW>
+__global__ void __launch_bounds__(TJ * 32, MINB)
 xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant__ CUtensorMap mS1,
                  const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
                  const __grid_constant__ CUtensorMap mC, const __grid_constant__ CUtensorMap mFd,
                  const __grid_constant__ CUtensorMap mFac, const X3Args a)
 {
+    using L = X3Lay<TJ, AROW>;
     constexpr int W = X3_W;
-    constexpr int TILE = TJ * W;                 // doubles per array per stage
-    constexpr int OFF_S = 0, OFF_A = TILE, OFF_C = 2 * TILE, OFF_FD = 3 * TILE, OFF_FAC = 4 * TILE, OFF_B = 5 * TILE;
-    constexpr int STAGE = 5 * TILE + (TJ + 1) * W;
-    constexpr uint32_t STAGE_BYTES = STAGE * sizeof(double);
+    constexpr int TILE = TJ * W;                 // doubles per exchange buffer
+    constexpr int STAGE = L::STAGE;
 
     extern __shared__ __align__(1024) unsigned char x3_smem[];
     double *ring = reinterpret_cast<double *>(x3_smem);
     double *X = ring + (size_t)K * STAGE;        // two exchange buffers of TILE doubles
     double *red_sum = X + 2 * TILE;              // [TJ]
     i64 *red_cnt = reinterpret_cast<i64 *>(red_sum + TJ);   // [TJ]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(red_cnt + TJ);   // [K]
-    int *box = reinterpret_cast<int *>(bars + K);            // [4] CTA-wide broadcasts
+    uint64_t *bars = reinterpret_cast<uint64_t *>(red_cnt + TJ);   // [2 K]: landed | free
+    int *box = reinterpret_cast<int *>(bars + 2 * K);        // [4] CTA-wide broadcasts
 
     const int lane = threadIdx.x & 31;
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // tile row of this warp (warp-uniform)
+    // Warp roles: the rows 0 and TJ-1 of a tile are never updated (their red results would be wrong and nothing
+    // reads them), so those two warps do not march: warp 0 is the TMA producer, warp TJ-1 is spare.
     if (threadIdx.x == 0) {
         #pragma unroll
-        for (int s = 0; s < K; ++s) xf_mbar_init(&bars[s], 1);
+        for (int s = 0; s < K; ++s) { xf_mbar_init(&bars[s], 1); xf_mbar_init(&bars[K + s], TJ - 2); }
         xf_fence_barrier_init();
     }
     __syncthreads();
@@ -104,17 +304,19 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
     const int nx = a.nx, ny = a.ny, nz = a.nz;
     const bool periodic = (a.bcx == XD_BC_PERIODIC);
     const bool extend = (a.bcy == XD_BC_EXTEND);
-    const int tps = a.ntx * a.nty;               // tiles per slice
+    const int tpl = a.ntx * a.nty;               // tiles per level range
+    const int tps = tpl * a.ntz;                 // tiles per slice
     const int total = tps * a.batch;
-    const double undef = a.undef, r2 = a.r2, r1 = a.r1;
-    const double2 zero2 = make_double2(0.0, 0.0);
-    unsigned q0 = 0;                             // levels consumed by this CTA so far (ring position)
+    X3Ring rg;
+    rg.cons = 0;
+    rg.phase = (w == 0) ? 0xffffffffu : 0u;      // producer: a fresh "free" barrier counts as completed (parity 1)
 
     for (int pp = 0; pp < a.npass; ++pp) {
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int b = tile / tps;
         const int tidx = tile - b * tps;
-        const int yb = tidx / a.ntx, xb = tidx - yb * a.ntx;
+        const int zb = tidx / tpl, trem = tidx - zb * tpl;
+        const int yb = trem / a.ntx, xb = trem - yb * a.ntx;
         // slice state: constant while any tile of the slice is still to do in this pass
         // (read through L2: another SM rewrites it between two passes of one launch)
         if (threadIdx.x == 0) { box[0] = __ldcg(&a.st[b].active); box[1] = __ldcg(&a.st[b].cur); }
@@ -123,123 +325,76 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
         __syncthreads();                         // box is rewritten by the next tile
         if (!active) continue;                   // frozen slice
 
-        const int x0 = xb * (W - 4), y0 = yb * a.RB;
+        const int x0 = xb * (W - 4), y0 = yb * a.RB;     // RB is even: the parity of a warp's row never changes
+        const int k0 = zb * a.ZB, k1 = min(k0 + a.ZB, nz);   // owned levels [k0, k1); ZB is even
+        const int kbase = (k0 >= 2) ? k0 - 2 : 0;            // first level loaded (even)
+        const int klast = min(k1 + 1, nz - 1);               // last level loaded
         const int j = y0 - 2 + w;                // global row of this warp
         const int gx = x0 - 2 + 2 * lane;        // global (even) column of this lane's pair
         const int bx = x0 - 2 + XM_PADL;         // padded x coordinate of the tile's first column
         const CUtensorMap *mS = cur ? &mS1 : &mS0;
         const bool own_row = (w >= 2) & (w < TJ - 2) & (j < ny);
         const bool own_lane = (lane >= 1) & (lane < 31);
-        const bool own_x = own_row & own_lane & (gx < nx);
-        const bool own_y = own_row & own_lane & (gx + 1 < nx);
-        const bool ghe = own_y & periodic & (gx < XM_GHOST);          // also write the east ghost copy
-        const bool ghw = own_y & periodic & (gx >= nx - XM_GHOST);    // also write the west ghost copy
-        const int wn = (w + 1 < TJ) ? W : 0, ws = (w > 0) ? -W : 0;  // rows beyond the tile only ever feed halo rows
-        double *const outS = a.Sbuf[cur ^ 1] + (i64)b * a.slice + (i64)j * a.pitch + XM_PADL + gx;
-        const int rowoff = w * W + 2 * lane;
+        X3Tile t;
+        t.own_x = own_row & own_lane & (gx < nx);
+        t.own_y = own_row & own_lane & (gx + 1 < nx);
+        t.ghe = t.own_y & periodic & (gx < XM_GHOST);          // also write the east ghost copy
+        t.ghw = t.own_y & periodic & (gx >= nx - XM_GHOST);    // also write the west ghost copy
+        // warp-uniform: this tile has single-column stores (odd nx) or ghost-column duty
+        t.edge = ((nx & 1) & (x0 + W - 2 > nx)) | (periodic & ((x0 < XM_GHOST + 2) | (x0 + W - 2 > nx - XM_GHOST)));
+        t.wn = (w + 1 < TJ) ? W : 0;             // rows beyond the tile only ever feed halo rows
+        t.ws = (w > 0) ? -W : 0;
+        t.ringrow = ring + w * W + 2 * lane;
+        t.arow = ring + L::OFF_A + w;
+        t.xrow = X + w * W + 2 * lane;
+        t.bars = bars;
+        t.plane = a.plane;
+        // step s brings level kbase + s; red works on level kbase + s - 1, black on kbase + s - 2
+        t.s_load = klast - kbase + 1;
+        t.s_red0 = max(1, k0 - 1) - kbase + 1;   t.s_red1 = min(nz - 2, k1) - kbase + 1;        // halo levels k0-1 and k1 too
+        t.s_blk0 = max(1, k0) - kbase + 2;       t.s_blk1 = min(nz - 2, k1 - 1) - kbase + 2;    // owned levels only
+        t.s_fin0 = k0 - kbase + 2;               t.s_fin1 = k1 - 1 - kbase + 2;
+        t.s_ext0 = 1 - kbase;                    t.s_ext1 = nz - 2 - kbase;
+        t.nsteps = t.s_fin1 + 1;
+        t.outp = a.Sbuf[cur ^ 1] + (i64)b * a.slice + (i64)(kbase - 2) * a.plane + (i64)j * a.pitch + XM_PADL + gx;
+        t.nx = nx; t.gx = gx;
+        t.periodic = periodic;
+        t.ext_j0 = extend & (j == 0); t.ext_jN = extend & (j == ny - 1);
+        t.ext_j1 = extend & (j == 1); t.ext_jM = extend & (j == ny - 2);
+        t.undef = a.undef; t.r2 = a.r2; t.r1 = a.r1;
 
-        auto issue = [&](int k) {                // thread 0: TMA loads of level k of this tile
-            const unsigned q = q0 + (unsigned)k;
-            double *dst = ring + (size_t)(q % K) * STAGE;
-            uint64_t *bar = &bars[q % K];
+        auto issue = [&](int s, int stage) {     // producer lane: TMA loads of the level of step s into `stage`
+            const int k = kbase + s;
+            double *dst = ring + (size_t)stage * STAGE;
+            uint64_t *bar = &bars[stage];
             const int ys = y0 - 2;
-            xf_mbar_expect_tx(bar, STAGE_BYTES);
-            xf_tma_load_3d(dst + OFF_S, mS, bar, bx, ys, b * nz + k);
-            xf_tma_load_3d(dst + OFF_A, &mA, bar, bx, ys, b * a.cbA * nz + k);
-            xf_tma_load_3d(dst + OFF_C, &mC, bar, bx, ys, b * a.cbC * nz + k);
-            xf_tma_load_3d(dst + OFF_FD, &mFd, bar, bx, ys, b * a.cbFd * nz + k);
-            xf_tma_load_3d(dst + OFF_FAC, &mFac, bar, bx, ys, b * a.cbFac * nz + k);
-            xf_tma_load_3d(dst + OFF_B, &mB, bar, bx, ys, b * a.cbB * nz + k);     // TJ+1 rows
+            xf_mbar_expect_tx(bar, L::TX_BYTES);
+            xf_tma_load_3d(dst + L::OFF_S, mS, bar, bx, ys, b * nz + k);                        // TJ rows
+            if (AROW) xf_tma_load_3d(dst + L::OFF_A, &mA, bar, ys, 0, b * a.cbA * nz + k);      // TJ row values (even start)
+            else      xf_tma_load_3d(dst + L::OFF_A, &mA, bar, bx, ys + 1, b * a.cbA * nz + k); // TJ-2 rows
+            xf_tma_load_3d(dst + L::OFF_C, &mC, bar, bx, ys + 1, b * a.cbC * nz + k);
+            xf_tma_load_3d(dst + L::OFF_FD, &mFd, bar, bx, ys + 1, b * a.cbFd * nz + k);
+            xf_tma_load_3d(dst + L::OFF_FAC, &mFac, bar, bx, ys + 1, b * a.cbFac * nz + k);
+            xf_tma_load_3d(dst + L::OFF_B, &mB, bar, bx, ys + 1, b * a.cbB * nz + k);           // TJ-1 rows
         };
-        if (threadIdx.x == 0) {
-            // every thread has finished reading the ring (barriers of the previous tile); order those
-            // generic-proxy reads before the async-proxy writes of the new loads
-            xf_fence_proxy_async();
-            const int pre = (nz < K - 1) ? nz : K - 1;
-            for (int k = 0; k < pre; ++k) issue(k);
-        }
-
-        double2 P1 = zero2, P2 = zero2, P3 = zero2;      // omega of levels s-1, s-2, s-3
-        double2 A1 = zero2, A2 = zero2;                  // A of levels s-1, s-2
-        double bBc = 0.0, bBn = 0.0, bCw = 0.0, bCe = 0.0, bFac = 0.0;   // operands of the black cell of level s-2
-        double bFd = xm_skip_value();
         double nsum = 0.0;
         int ncnt = 0;
-
-        for (int s = 0; s < nz + 2; ++s) {
-            // ---- level s arrives ----
-            double2 Pn = zero2, An = zero2;
-            if (s < nz) {
-                const unsigned q = q0 + (unsigned)s;
-                xf_mbar_wait(&bars[q % K], (q / K) & 1u);
-                const double *g = ring + (size_t)(q % K) * STAGE + rowoff;
-                Pn = x3_ld2(g + OFF_S);
-                An = x3_ld2(g + OFF_A);
-                if (extend & (s >= 1) & (s <= nz - 2)) {           // numbas.py:87-115: levels 1..nz-2 only
-                    if (j == 0) Pn = xm_extend(Pn, x3_ld2(g + OFF_S + W), gx, nx, periodic, undef);
-                    if (j == ny - 1) Pn = xm_extend(Pn, x3_ld2(g + OFF_S - W), gx, nx, periodic, undef);
+        if (w == 0) {
+            // producer: one level per stage, as far ahead as the ring allows
+            for (int s = 0; s < t.s_load; ++s) {
+                xf_mbar_wait(&bars[K + rg.cons], (rg.phase >> rg.cons) & 1u);    // the compute warps are done with the stage
+                rg.phase ^= (1u << rg.cons);
+                if (lane == 0) {
+                    xf_fence_proxy_async();      // their generic-proxy reads before the async-proxy writes
+                    issue(s, rg.cons);
                 }
+                rg.cons = (rg.cons + 1 == K) ? 0 : rg.cons + 1;
+                __syncwarp();
             }
-            // ---- red cells of level s-1 (neighbours in y: the staged level, still untouched) ----
-            const int kr = s - 1;
-            // operands of the black cell of level s-1: used by the black half step of the NEXT step
-            double nBc = 0.0, nBn = 0.0, nCw = 0.0, nCe = 0.0, nFac = 0.0, nFd = xm_skip_value();
-            if ((kr >= 1) & (kr <= nz - 2)) {
-                const unsigned q = q0 + (unsigned)kr;
-                const double *r = ring + (size_t)(q % K) * STAGE + rowoff;
-                const double2 Bc = x3_ld2(r + OFF_B), Bn = x3_ld2(r + OFF_B + W), Cc = x3_ld2(r + OFF_C);
-                const double2 Fd = x3_ld2(r + OFF_FD), Fc = x3_ld2(r + OFF_FAC);
-                double2 Sn = x3_ld2(r + OFF_S + wn), Ss = x3_ld2(r + OFF_S + ws);
-                if (extend) {
-                    // the extended boundary row as the cells of rows 1 / ny-2 see it: their own old value
-                    if (j == 1) { if (P1.x != undef) Ss.x = P1.x; if (P1.y != undef) Ss.y = P1.y; }
-                    if (j == ny - 2) { if (P1.x != undef) Sn.x = P1.x; if (P1.y != undef) Sn.y = P1.y; }
-                }
-                const double Cnext = xm_shfl_down1(Cc.x);          // C of the column east of the pair
-                if (((j + kr) & 1) == 0) {                         // red = the even column of the pair
-                    const double nb = xm_shfl_up1(P1.y);
-                    P1.x = x3_cell(P1.x, Pn.x, P2.x, Sn.x, Ss.x, P1.y, nb, An.x, A1.x, Bn.x, Bc.x, Cc.y, Cc.x, Fd.x, Fc.x, r2, r1);
-                    nBc = Bc.y; nBn = Bn.y; nCw = Cc.y; nCe = Cnext; nFd = Fd.y; nFac = Fc.y;
-                } else {
-                    const double nb = xm_shfl_down1(P1.x);
-                    P1.y = x3_cell(P1.y, Pn.y, P2.y, Sn.y, Ss.y, nb, P1.x, An.y, A1.y, Bn.y, Bc.y, Cnext, Cc.y, Fd.y, Fc.y, r2, r1);
-                    nBc = Bc.x; nBn = Bn.x; nCw = Cc.x; nCe = Cc.y; nFd = Fd.x; nFac = Fc.x;
-                }
-            }
-            // publish the row (red cells final for this iteration) for the black half step of the next step
-            *reinterpret_cast<double2 *>(X + (size_t)(s & 1) * TILE + rowoff) = P1;
-            // ---- black cells of level s-2 (neighbours in y: rows published in the previous step) ----
-            const int kb = s - 2;
-            if ((kb >= 1) & (kb <= nz - 2)) {
-                const double *xr = X + (size_t)((s - 1) & 1) * TILE + rowoff;
-                const double2 Sn = x3_ld2(xr + wn), Ss = x3_ld2(xr + ws);
-                if (((j + kb) & 1) == 1) {                         // black = the even column of the pair
-                    const double nb = xm_shfl_up1(P2.y);
-                    P2.x = x3_cell(P2.x, P1.x, P3.x, Sn.x, Ss.x, P2.y, nb, A1.x, A2.x, bBn, bBc, bCe, bCw, bFd, bFac, r2, r1);
-                } else {
-                    const double nb = xm_shfl_down1(P2.x);
-                    P2.y = x3_cell(P2.y, P1.y, P3.y, Sn.y, Ss.y, nb, P2.x, A1.y, A2.y, bBn, bBc, bCe, bCw, bFd, bFac, r2, r1);
-                }
-            }
-            // ---- level s-2 is complete: norm over owned cells (numbas.py:1689-1708), store ----
-            if ((kb >= 0) & (kb <= nz - 1)) {
-                xm_norm_acc_lane(nsum, ncnt, P2.x, own_x, undef);
-                xm_norm_acc_lane(nsum, ncnt, P2.y, own_y, undef);
-                if ((kb >= 1) & (kb <= nz - 2)) {                  // levels 0 and nz-1 never change
-                    double *dst = outS + (i64)kb * a.plane;
-                    xm_store2_if(own_y, dst, P2);
-                    xm_store1_if(own_x & !own_y, dst, P2.x);       // odd nx: the last column stands alone
-                    xm_store2_if(ghe, dst + nx, P2);
-                    xm_store2_if(ghw, dst - nx, P2);
-                }
-            }
-            __syncthreads();                     // rows published; stage of level s-1 free
-            if (threadIdx.x == 0 && s + K - 1 < nz) { xf_fence_proxy_async(); issue(s + K - 1); }
-            P3 = P2; P2 = P1; P1 = Pn;
-            A2 = A1; A1 = An;
-            bBc = nBc; bBn = nBn; bCw = nCw; bCe = nCe; bFd = nFd; bFac = nFac;
+        } else if (w < TJ - 1) {
+            if (w & 1) x3_march<TJ, K, AROW, true>(t, rg, nsum, ncnt);
+            else       x3_march<TJ, K, AROW, false>(t, rg, nsum, ncnt);
         }
-        q0 += (unsigned)nz;
 
         // ---- per-tile norm partial, ticket, loop control by the last tile of the slice ----
         #pragma unroll
@@ -371,6 +526,25 @@ __global__ void x3_pack_derived_kernel(double *__restrict__ Fd, double *__restri
     }
 }
 
+// AROW detection: flag[0] |= 1 if some X[row][i] differs (bitwise) from X[row][0]
+__global__ void x3_rowconst_kernel(const double *__restrict__ X, i64 rows, i64 nx, int *flag)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nx) return;
+    const long long *P = reinterpret_cast<const long long *>(X);
+    int bad = 0;
+    for (i64 row = blockIdx.y; row < rows; row += gridDim.y) bad |= (P[row * nx + i] != P[row * nx]);
+    if (bad) flag[0] = 1;
+}
+// AROW operand: vals[v][j] = A[v][j][0] for every (volume x level) v, row pitch rpitch
+__global__ void x3_pack_rowvals_kernel(double *__restrict__ vals, const double *__restrict__ A, i64 nv, i64 ny, i64 nx,
+                                       i64 rpitch)
+{
+    const i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rpitch) return;
+    for (i64 v = blockIdx.y; v < nv; v += gridDim.y) vals[v * rpitch + j] = (j < ny) ? A[(v * ny + j) * nx] : 0.0;
+}
+
 __global__ void x3_unpack_kernel(double *__restrict__ dst, const double *__restrict__ buf0,
                                  const double *__restrict__ buf1, i64 rows, i64 nx, i64 pitch, i64 nb,
                                  const XdSliceState *__restrict__ st)
@@ -387,19 +561,30 @@ __global__ void x3_unpack_kernel(double *__restrict__ dst, const double *__restr
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
-struct X3Variant { int TJ, K; };
+// kernel variants: tile height TJ (TJ - 4 owned rows, TJ warps), ring depth K, CTAs per SM the register
+// budget is cut for.  Shared memory per CTA = K stages of (6 TJ - 9) rows of 512 bytes (AROW: 5 TJ - 7)
+// + 2 exchange buffers of TJ rows.
+struct X3Variant { int TJ, K, MINB; };
 static const X3Variant X3_VARIANTS[] = {
-    {16, 4},   // 0: 12 owned rows per tile, 512 threads, 210 KB
-    {12, 4},   // 1:  8 owned rows, 384 threads, 158 KB
-    {8, 4},    // 2:  4 owned rows, 256 threads, 106 KB (tiny grids)
-    {16, 3},   // 3: shallower ring
-    {12, 3},   // 4
+    {16, 4, 1},   // 0: 12 owned rows, 512 threads, 190 KB: large volumes
+    {12, 4, 1},   // 1:  8 owned rows, 384 threads, 138 KB
+    {12, 3, 2},   // 2:  8 owned rows, 2 CTAs per SM (24 warps), 106 KB each
+    {8, 3, 3},    // 3:  4 owned rows, 3 CTAs per SM (24 warps), 67 KB each
+    {8, 4, 2},    // 4:  4 owned rows, 2 CTAs per SM, 87 KB each
+    {16, 3, 1},   // 5: 12 owned rows, shallower ring, 146 KB
+    {12, 5, 1},   // 6: deeper rings
+    {12, 6, 1},   // 7
+    {8, 8, 1},    // 8
+    {8, 5, 2},    // 9
+    {20, 3, 1},   // 10: 16 owned rows, 640 threads
+    {24, 2, 1},   // 11
 };
 #define X3_NVARIANTS ((int)(sizeof(X3_VARIANTS) / sizeof(X3_VARIANTS[0])))
 
 struct Fused3Plan {
     bool built = false;
     int variant = 0;
+    bool arow = false;             // A constant along x: AROW kernels
     bool coop = false;
     int ppl = 1;
     unsigned long long gbar_base = 0;
@@ -423,21 +608,21 @@ static inline bool fused3_plan_supported(const XdGeom &g, std::string &why)
     return true;
 }
 
-template <int TJ, int K>
+template <int TJ, int K, bool AROW>
 static size_t x3_smem_bytes()
 {
-    const size_t stage = (size_t)(5 * TJ * X3_W + (TJ + 1) * X3_W) * sizeof(double);
-    return (size_t)K * stage + (size_t)2 * TJ * X3_W * sizeof(double) + (size_t)TJ * 16 + (size_t)K * 8 + 16;
+    const size_t stage = (size_t)X3Lay<TJ, AROW>::STAGE * sizeof(double);
+    return (size_t)K * stage + (size_t)2 * TJ * X3_W * sizeof(double) + (size_t)TJ * 16 + (size_t)K * 16 + 16;
 }
-template <int TJ, int K>
+template <int TJ, int K, int MINB, bool AROW>
 static cudaError_t x3_prepare(size_t *smem, int *blocks_per_sm)
 {
-    *smem = x3_smem_bytes<TJ, K>();
-    cudaError_t e = cudaFuncSetAttribute(xm3_std3d_kernel<TJ, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+    *smem = x3_smem_bytes<TJ, K, AROW>();
+    cudaError_t e = cudaFuncSetAttribute(xm3_std3d_kernel<TJ, K, MINB, AROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, xm3_std3d_kernel<TJ, K>, TJ * 32, *smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, xm3_std3d_kernel<TJ, K, MINB, AROW>, TJ * 32, *smem);
 }
-template <int TJ, int K>
+template <int TJ, int K, int MINB, bool AROW>
 static cudaError_t x3_launch(const Fused3Plan &p, cudaStream_t stream)
 {
     cudaLaunchConfig_t cfg = {};
@@ -450,34 +635,47 @@ static cudaError_t x3_launch(const Fused3Plan &p, cudaStream_t stream)
     attr[0].val.cooperative = (p.args.npass > 1) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, xm3_std3d_kernel<TJ, K>, p.mS[0], p.mS[1], p.mA, p.mB, p.mC, p.mFd, p.mFac, p.args);
+    return cudaLaunchKernelEx(&cfg, xm3_std3d_kernel<TJ, K, MINB, AROW>, p.mS[0], p.mS[1], p.mA, p.mB, p.mC, p.mFd, p.mFac, p.args);
 }
 
-#define X3_DISPATCH(v, CALL)              \
-    switch (v) {                          \
-    case 0: CALL(16, 4); break;           \
-    case 1: CALL(12, 4); break;           \
-    case 2: CALL(8, 4); break;            \
-    case 3: CALL(16, 3); break;           \
-    default: CALL(12, 3); break;          \
+#define X3_DISPATCH1(v, AR, CALL)                     \
+    switch (v) {                                      \
+    case 0: CALL(16, 4, 1, AR); break;                \
+    case 1: CALL(12, 4, 1, AR); break;                \
+    case 2: CALL(12, 3, 2, AR); break;                \
+    case 3: CALL(8, 3, 3, AR); break;                 \
+    case 4: CALL(8, 4, 2, AR); break;                 \
+    case 5: CALL(16, 3, 1, AR); break;                \
+    case 6: CALL(12, 5, 1, AR); break;                \
+    case 7: CALL(12, 6, 1, AR); break;                \
+    case 8: CALL(8, 8, 1, AR); break;                 \
+    case 9: CALL(8, 5, 2, AR); break;                 \
+    case 10: CALL(20, 3, 1, AR); break;               \
+    default: CALL(24, 2, 1, AR); break;               \
     }
+#define X3_DISPATCH(v, arow, CALL) if (arow) { X3_DISPATCH1(v, true, CALL) } else { X3_DISPATCH1(v, false, CALL) }
 
-// tile height: as few halo rows as possible while the tiles still fill the SMs evenly
-static int x3_choose_variant(i64 ny, i64 nx, i64 batch, int sm_count)
+// Tile shape.  Measured on B200 (37 x 180 x 360 and 300 x 300 x 602 volumes): a step of the march costs about
+// 0.83 us with 16-row tiles (ring of 4), 0.72 us with 12-row tiles (ring of 5) and 0.78 us with two co-resident
+// 8-row tiles per SM (ring of 5) -- nearly independent of the volume -- so the cost of a pass is about
+// (rounds of tiles over the SM slots) x (levels + drain + pipeline fill) x that.  Splitting the levels over
+// several tiles (XINV_FUSED3_NTZ) never won in the measurements and is off by default.
+static void x3_choose(i64 nz, i64 ny, i64 nx, i64 batch, int sm_count, int *variant, int *ntz)
 {
     const i64 ntx = (nx + X3_W - 5) / (X3_W - 4);
-    double best = -1.0;
-    int bestv = 0;
-    for (int v = 0; v < 3; ++v) {
-        const int RB = X3_VARIANTS[v].TJ - 4;
+    static const int cand[] = {0, 6, 9};
+    static const double t_step[] = {0.83, 0.72, 0.78};
+    double best = 1e300;
+    *variant = 0; *ntz = 1;
+    for (int ci = 0; ci < 3; ++ci) {
+        const X3Variant v = X3_VARIANTS[cand[ci]];
+        const int RB = v.TJ - 4;
         const i64 tiles = ntx * ((ny + RB - 1) / RB) * batch;
-        const i64 rounds = (tiles + sm_count - 1) / sm_count;
-        // useful rows per tile row x how evenly the tiles fill the SMs; a taller tile also spends more
-        // shared-memory and FP64 cycles per step on one SM, which the first factor already prices in
-        const double eff = ((double)RB / (double)X3_VARIANTS[v].TJ) * ((double)tiles / (double)(rounds * sm_count));
-        if (eff > best + 1e-9) { best = eff; bestv = v; }
+        const double slots = (double)sm_count * v.MINB;
+        const double rounds = (tiles <= slots) ? 1.0 : (double)tiles / slots;
+        const double cost = rounds * ((double)nz + 5.0) * t_step[ci];
+        if (cost < best - 1e-9) { best = cost; *variant = cand[ci]; }
     }
-    return bestv;
 }
 
 static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, const XdGeom &g, const XdCoef &q, i64 batch,
@@ -503,49 +701,75 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
     (ptr) = work.p[idx];
     X3_ALLOC(p.bufS[0], 0, vol_bytes * batch);
     X3_ALLOC(p.bufS[1], 1, vol_bytes * batch);
-    X3_ALLOC(p.bufA, 2, vol_bytes * (cb[0] ? batch : 1));
+    void *flag;
+    X3_ALLOC(flag, 7, 16);
+    dim3 blk(128);
+    auto gridfor = [&](i64 cols, i64 nrows) {
+        i64 gy = nrows;
+        if (gy > 32768) gy = 32768;
+        return dim3((unsigned)((cols + 127) / 128), (unsigned)gy, 1);
+    };
+    // ---- is A constant along x?  (one pass over it, one 4-byte read-back) ----
+    {
+        const char *ea = getenv("XINV_FUSED3_AROW");
+        p.arow = !(ea && atoi(ea) == 0);
+        if (p.arow) {
+            const i64 nrA = rows * (cb[0] ? batch : 1);
+            cudaMemsetAsync(flag, 0, 4, stream);
+            x3_rowconst_kernel<<<gridfor(nx, nrA), blk, 0, stream>>>(q.c[0], nrA, nx, (int *)flag);
+            int h = 1;
+            if ((e = cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+                (e = cudaStreamSynchronize(stream)) != cudaSuccess) {
+                why = std::string("row-constancy check: ") + cudaGetErrorString(e);
+                fused3_plan_release(p);
+                return -1;
+            }
+            p.arow = (h == 0);
+        }
+    }
+    const i64 rpitch = (ny + 1) / 2 * 2;         // row-value vectors: TMA strides are multiples of 16 bytes
+    const i64 nvA = nz * (cb[0] ? batch : 1);    // (volume x level) planes of A
+    X3_ALLOC(p.bufA, 2, p.arow ? (size_t)nvA * rpitch * sizeof(double) : vol_bytes * (cb[0] ? batch : 1));
     X3_ALLOC(p.bufC, 3, vol_bytes * (cb[2] ? batch : 1));
     X3_ALLOC(p.bufFd, 4, vol_bytes * (cbFd ? batch : 1));
     X3_ALLOC(p.bufFac, 5, vol_bytes * (cbFac ? batch : 1));
     X3_ALLOC(p.bufB, 6, vol_bytes * (cb[1] ? batch : 1));
-    void *flag;
-    X3_ALLOC(flag, 7, 16);
 #undef X3_ALLOC
+    int ntz = 1;
     {
+        x3_choose(nz, ny, nx, batch, sm_count, &p.variant, &ntz);
         const char *env = getenv("XINV_FUSED3_VARIANT");
-        p.variant = env ? atoi(env) : x3_choose_variant(ny, nx, batch, sm_count);
+        if (env) { p.variant = atoi(env); ntz = 1; }
         if (p.variant < 0 || p.variant >= X3_NVARIANTS) p.variant = 0;
+        const char *ez = getenv("XINV_FUSED3_NTZ");
+        if (ez && atoi(ez) > 0) ntz = atoi(ez);
     }
     const X3Variant v = X3_VARIANTS[p.variant];
-    dim3 blk(128);
-    auto gridfor = [&](i64 cols, i64 nb) {
-        i64 gy = rows * nb;
-        if (gy > 32768) gy = 32768;
-        return dim3((unsigned)((cols + 127) / 128), (unsigned)gy, 1);
-    };
     auto pack = [&](void *dst, const double *src, i64 bstride, i64 nb) {
-        x3_pack_kernel<<<gridfor(pitch, nb), blk, 0, stream>>>((double *)dst, src, rows, nx, pitch, bstride, nb, periodic);
+        x3_pack_kernel<<<gridfor(pitch, rows * nb), blk, 0, stream>>>((double *)dst, src, rows, nx, pitch, bstride, nb, periodic);
     };
     pack(p.bufS[0], dS, g.N, batch);
     pack(p.bufS[1], dS, g.N, batch);       // levels 0 / nz-1 and all pad columns of both buffers start identical
-    pack(p.bufA, q.c[0], q.cs[0], cb[0] ? batch : 1);
+    if (p.arow) x3_pack_rowvals_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, q.c[0], nvA, ny, nx, rpitch);
+    else        pack(p.bufA, q.c[0], q.cs[0], cb[0] ? batch : 1);
     pack(p.bufB, q.c[1], q.cs[1], cb[1] ? batch : 1);
     pack(p.bufC, q.c[2], q.cs[2], cb[2] ? batch : 1);
-    x3_pack_derived_kernel<<<gridfor(pitch, cbFd ? batch : 1), blk, 0, stream>>>(
+    x3_pack_derived_kernel<<<gridfor(pitch, rows * (cbFd ? batch : 1)), blk, 0, stream>>>(
         (double *)p.bufFd, (double *)p.bufFac, q, nz, ny, nx, pitch, cbFd ? batch : 1, cbFac ? batch : 1, periodic);
     if ((e = cudaGetLastError()) != cudaSuccess) {
         why = std::string("pack kernels: ") + cudaGetErrorString(e);
         fused3_plan_release(p);
         return -1;
     }
-    // tensor maps: (pitch, ny, levels x volumes), box 64 x TJ (B: TJ+1) x 1
+    // tensor maps: (pitch, ny, levels x volumes); boxes 64 columns x TJ rows (omega), TJ-1 (B), TJ-2 (A, C, Fd, fac)
     if (xf_make_map(&p.mS[0], p.bufS[0], pitch, ny, nz * batch, X3_W, v.TJ, why) ||
         xf_make_map(&p.mS[1], p.bufS[1], pitch, ny, nz * batch, X3_W, v.TJ, why) ||
-        xf_make_map(&p.mA, p.bufA, pitch, ny, nz * (cb[0] ? batch : 1), X3_W, v.TJ, why) ||
-        xf_make_map(&p.mB, p.bufB, pitch, ny, nz * (cb[1] ? batch : 1), X3_W, v.TJ + 1, why) ||
-        xf_make_map(&p.mC, p.bufC, pitch, ny, nz * (cb[2] ? batch : 1), X3_W, v.TJ, why) ||
-        xf_make_map(&p.mFd, p.bufFd, pitch, ny, nz * (cbFd ? batch : 1), X3_W, v.TJ, why) ||
-        xf_make_map(&p.mFac, p.bufFac, pitch, ny, nz * (cbFac ? batch : 1), X3_W, v.TJ, why)) {
+        (p.arow ? xf_make_row_map(&p.mA, p.bufA, ny, rpitch, nvA, v.TJ, 1, why)
+                : xf_make_map(&p.mA, p.bufA, pitch, ny, nvA, X3_W, v.TJ - 2, why)) ||
+        xf_make_map(&p.mB, p.bufB, pitch, ny, nz * (cb[1] ? batch : 1), X3_W, v.TJ - 1, why) ||
+        xf_make_map(&p.mC, p.bufC, pitch, ny, nz * (cb[2] ? batch : 1), X3_W, v.TJ - 2, why) ||
+        xf_make_map(&p.mFd, p.bufFd, pitch, ny, nz * (cbFd ? batch : 1), X3_W, v.TJ - 2, why) ||
+        xf_make_map(&p.mFac, p.bufFac, pitch, ny, nz * (cbFac ? batch : 1), X3_W, v.TJ - 2, why)) {
         fused3_plan_release(p);
         return -1;
     }
@@ -557,18 +781,21 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
     a.RB = v.TJ - 4;
     a.ntx = (int)((nx + X3_W - 5) / (X3_W - 4));
     a.nty = (int)((ny + a.RB - 1) / a.RB);
+    if (ntz < 1) ntz = 1;
+    a.ZB = (int)((nz + ntz - 1) / ntz);
+    a.ZB += (a.ZB & 1);                         // level ranges start on even levels
+    if (a.ZB < 2) a.ZB = 2;
+    a.ntz = (int)((nz + a.ZB - 1) / a.ZB);
     a.batch = (int)batch;
     a.bcy = g.bcy; a.bcx = g.bcx;
     a.cbA = cb[0]; a.cbB = cb[1]; a.cbC = cb[2]; a.cbFd = cbFd; a.cbFac = cbFac;
     a.r2 = q.p[1]; a.r1 = q.p[2]; a.undef = q.undef;
     p.batch = batch;
-    p.nblk_partials = a.ntx * a.nty;
-    const i64 tiles = (i64)a.ntx * a.nty * batch;
-    p.grid = (int)(tiles < sm_count ? tiles : sm_count);
-    if (p.grid < 1) p.grid = 1;
+    p.nblk_partials = a.ntx * a.nty * a.ntz;
+    const i64 tiles = (i64)a.ntx * a.nty * a.ntz * batch;
     int blocks_per_sm = 0;
-#define X3_PREP(TJ_, K_) e = x3_prepare<TJ_, K_>(&p.smem, &blocks_per_sm)
-    X3_DISPATCH(p.variant, X3_PREP);
+#define X3_PREP(TJ_, K_, MB_, AR_) e = x3_prepare<TJ_, K_, MB_, AR_>(&p.smem, &blocks_per_sm)
+    X3_DISPATCH(p.variant, p.arow, X3_PREP);
 #undef X3_PREP
     if (e != cudaSuccess || blocks_per_sm < 1) {
         why = std::string("3-D fused kernel does not fit: ") + cudaGetErrorString(e);
@@ -576,10 +803,13 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
         return -1;
     }
     {
+        const i64 slots = (i64)sm_count * blocks_per_sm;
+        p.grid = (int)(tiles < slots ? tiles : slots);
+        if (p.grid < 1) p.grid = 1;
         int can_coop = 0, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&can_coop, cudaDevAttrCooperativeLaunch, dev);
-        p.coop = can_coop && ((i64)blocks_per_sm * sm_count >= p.grid);
+        p.coop = can_coop != 0;
         const char *eppl = getenv("XINV_FUSED_PPL");
         p.ppl = p.coop ? (eppl ? atoi(eppl) : 32) : 1;
         if (p.ppl < 1) p.ppl = 1;
@@ -603,11 +833,11 @@ static inline int fused3_sweep(Fused3Plan &p, cudaStream_t stream, XdSliceState 
     a.st = st; a.psum = psum; a.pcnt = pcnt; a.ticket = ticket; a.nactive = nactive;
     a.tol = tol; a.mxLoop = mxLoop;
     cudaError_t e = cudaSuccess;
-#define X3_GO(TJ_, K_) e = x3_launch<TJ_, K_>(p, stream)
+#define X3_GO(TJ_, K_, MB_, AR_) e = x3_launch<TJ_, K_, MB_, AR_>(p, stream)
     if (npass > 1) {
         a.npass = npass;
         a.gbar_base = p.gbar_base;
-        X3_DISPATCH(p.variant, X3_GO);
+        X3_DISPATCH(p.variant, p.arow, X3_GO);
         if (e == cudaSuccess) {
             p.gbar_base += (unsigned long long)p.grid * (unsigned long long)(npass - 1);
             *launches += 1;
@@ -620,7 +850,7 @@ static inline int fused3_sweep(Fused3Plan &p, cudaStream_t stream, XdSliceState 
     a.npass = 1;
     a.gbar_base = p.gbar_base;
     for (int n = 0; n < npass; ++n) {
-        X3_DISPATCH(p.variant, X3_GO);
+        X3_DISPATCH(p.variant, p.arow, X3_GO);
         if (e != cudaSuccess) return -1;
         *launches += 1;
     }
