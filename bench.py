@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py -- grid-cell-updates/s of the SOR sweep on B200 (+ CPU reference arm).
+"""bench.py -- grid-cell-updates/s of the SOR sweep + iterations-to-tolerance on B200 (+ CPU reference arm).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload c2|c1|c5] [--sweeps M] [--engine auto|colour|fused]
@@ -20,6 +20,15 @@ e2e    = the same steps through the public API, the call a user of xinvert makes
          coefficients / de-masking on the device, D2H of psi; all inside the timed region).
 e2e_cabi = the same through the C-ABI entry that mirrors the reference's core.inv_standard2D
          boundary, xinv_std2d with full host arrays: H2D of S, A, C, F and D2H of S every step.
+iters_to_tol = the other half of BASELINE.json's metric: sweeps until the reference's stop test
+         fires (numbas.py:401-414), for the reference's lexicographic order on the CPU, the same
+         order on the GPU and the GPU's red-black order, at the same omega and tolerance, with
+         the largest relative difference between the converged fields (C1 and C2).
+configs = the other BASELINE.json configs (c1, c3, c4, c5 and the reference notebook's omega
+         case) measured in the same process after the headline: sweep-loop rate, us per sweep,
+         roofline fraction of the sweep kernel.
+configs4 (N > 1) = BASELINE configs[4] exactly: 256 time slices of 1440x720 cut over the N ranks
+         with distributed.shard_bounds, sweep-loop value and e2e through invert_Poisson.
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -36,6 +45,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+import synthetic  # noqa: E402
+
 METRIC = "grid-cell-updates/sec (SOR sweep)"
 UNIT = "cell-updates/s"
 UNDEF = -9.99e8
@@ -49,6 +60,7 @@ WORKLOADS = {
     "c5": (720, 1440, 32, ("fixed", "periodic"),
            "configs[4]: batched invert_Poisson 1440x720, 32 time slices per GPU"),
 }
+C5_TOTAL_SLICES = 256               # BASELINE configs[4]
 
 
 def env_rank():
@@ -56,13 +68,14 @@ def env_rank():
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
-def make_problem(name, rank, pinned=False):
+def make_problem(name, rank, pinned=False, slices=None, first_slice=None):
     """Synthetic operands of one rank's shard (SURVEY.md 8d recipes)."""
-    from tests import cases
     import xinvert_b200 as xb
     ny, nx, per_gpu, bcs, _ = WORKLOADS[name]
-    c = cases.poisson_latlon(ny, nx, land=(name != "c1"), noise=1e-6, seed=1000 + rank,
-                             batch=per_gpu if per_gpu > 1 else None, phase=0.37 * rank)
+    if slices is not None:
+        per_gpu = slices
+    c = synthetic.poisson_latlon(ny, nx, land=(name != "c1"), noise=1e-6, seed=1000 + rank,
+                                 batch=per_gpu if per_gpu > 1 else None, phase=0.37 * rank)
     if name == "c1":
         c["p"]["optArg"] = 1.4
     if pinned:
@@ -71,6 +84,18 @@ def make_problem(name, rank, pinned=False):
             buf[...] = c[k]
             c[k] = buf
     return c, bcs
+
+
+def run_std2d(mod, c, bcy, bcx, mxLoop, tol, omega=None, **kw):
+    """``mod.invert_standard_2D`` (the reference's numba kernel, its C port, or the CUDA shim: one
+    positional signature, numbas.py:216-219) on case c; returns (S, flags)."""
+    p = c["p"]
+    S = np.array(c["S0"], dtype=np.float64, copy=True)
+    fl = np.array([0.0, 1.0, 0.0])
+    mod.invert_standard_2D(S, c["A"], c.get("B"), c["C"], c["F"], p["gc2"], p["gc1"], p["del2"], p["del1"], bcy, bcx,
+                           p["del1Sqr"], p["ratioQtr"], p["ratioSqr"], p["optArg"] if omega is None else omega, UNDEF, fl,
+                           mxLoop, tol, **kw)
+    return S, fl
 
 
 # ---------------------------------------------------------------------------
@@ -141,21 +166,36 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-def cpu_case(name, rank=0):
-    """One slice of this rank's shard as the C oracle wants it (2-D arrays)."""
+# CPU legs: the reference's own numba kernels when oracle/_ref (or /root/reference) holds them, else
+# the C port that is pinned bit-exact to them
+# ---------------------------------------------------------------------------
+def cpu_impl(prefer_reference=True):
+    """(kind, module): ('reference', the unmodified numbas.py) or ('port', the C oracle)."""
+    import oracle
+    if prefer_reference and os.environ.get("XINV_BENCH_CPU", "") != "port":
+        try:
+            from oracle import ref_loader
+            if ref_loader.available():
+                return "reference", ref_loader.ref_numbas()
+        except Exception:
+            pass
+    return "port", oracle
+
+
+def cpu_case(name, rank=0, kind="port"):
+    """One slice of this rank's shard as the CPU kernels want it (2-D arrays; the numba kernel needs B as
+    an array of zeros -- what apps.py:1407 passes -- the C port takes B = None for the same arithmetic)."""
     c, bcs = make_problem(name, rank)
     S0 = c["S0"] if c["S0"].ndim == 2 else c["S0"][0]
     F = c["F"] if c["F"].ndim == 2 else c["F"][0]
-    return dict(A=c["A"], C=c["C"], F=F, S0=S0, p=c["p"]), bcs
+    return dict(A=c["A"], B=np.zeros_like(c["A"]) if kind == "reference" else None, C=c["C"], F=np.ascontiguousarray(F),
+                S0=S0, p=c["p"]), bcs
 
 
-def cpu_solve(case, bcs, sweeps):
-    """`sweeps` lexicographic SOR sweeps (numbas.py:215-416) through the C oracle port on the
-    calling thread; returns the seconds spent in the solve."""
-    import oracle
-    from tests import cases
+def cpu_solve(mod, case, bcs, sweeps):
+    """`sweeps` lexicographic SOR sweeps (numbas.py:215-416) on the calling thread; seconds spent in the solve."""
     t0 = time.perf_counter()
-    _, fl = cases.run_std2d(oracle, case, bcs[0], bcs[1], sweeps - 1, -1.0)
+    _, fl = run_std2d(mod, case, bcs[0], bcs[1], sweeps - 1, -1.0)
     dt = time.perf_counter() - t0
     assert int(fl[2]) + 1 == sweeps
     return dt
@@ -164,10 +204,11 @@ def cpu_solve(case, bcs, sweeps):
 def cpu_reference_rate(name, sweeps, rank=0):
     """Reference algorithm on ONE host thread -- the reference is single-threaded by
     construction and one slice cannot use more."""
-    case, bcs = cpu_case(name, rank)
-    cpu_solve(case, bcs, 1)                                          # warm caches / page in
-    dt = cpu_solve(case, bcs, sweeps)
-    return sweeps * case["S0"].size / dt, dt
+    kind, mod = cpu_impl()
+    case, bcs = cpu_case(name, rank, kind)
+    cpu_solve(mod, case, bcs, 1)                                     # JIT / warm caches / page in
+    dt = cpu_solve(mod, case, bcs, sweeps)
+    return kind, sweeps * case["S0"].size / dt, dt
 
 
 _REF_JOB = None
@@ -176,8 +217,10 @@ _REF_JOB = None
 def _ref_worker_init(workload, world):
     global _REF_JOB
     ident = mp_ident()
-    _REF_JOB = cpu_case(workload, ident % world)
-    cpu_solve(_REF_JOB[0], _REF_JOB[1], 1)
+    kind, mod = cpu_impl()
+    case, bcs = cpu_case(workload, ident % world, kind)
+    _REF_JOB = (mod, case, bcs, kind)
+    cpu_solve(mod, case, bcs, 1)
 
 
 def mp_ident():
@@ -187,11 +230,11 @@ def mp_ident():
 
 
 def _ref_worker_solve(nsw):
-    return cpu_solve(_REF_JOB[0], _REF_JOB[1], nsw)
+    return cpu_solve(_REF_JOB[0], _REF_JOB[1], _REF_JOB[2], nsw), _REF_JOB[3]
 
 
 def run_reference(args):
-    """The reference's own algorithm on the host cores: every slice is an independent,
+    """The reference's own implementation on the host cores: every slice is an independent,
     inherently serial solve (lexicographic Gauss-Seidel), so the job -- one slice per GPU for
     c2/c1, 32 per GPU for c5 -- can use one host thread per slice and no more."""
     rank, _, world = env_rank()
@@ -205,9 +248,12 @@ def run_reference(args):
     # one worker process per slice (each builds its own slice once, then only solves)
     pool = mp.get_context("fork").Pool(nthreads, initializer=_ref_worker_init, initargs=(args.workload, max(1, world)))
 
+    kinds = set()
+
     def step(nsw):
         t0 = time.perf_counter()
-        pool.map(_ref_worker_solve, [nsw] * nthreads, chunksize=1)
+        for _, k in pool.map(_ref_worker_solve, [nsw] * nthreads, chunksize=1):
+            kinds.add(k)
         return time.perf_counter() - t0
 
     for _ in range(args.warmup):
@@ -215,17 +261,136 @@ def run_reference(args):
     times = [step(sweeps) for _ in range(args.steps)]
     value = nthreads * sweeps * ny * nx * args.steps / sum(times)
     pool.close()
+    kind = "reference" if kinds == {"reference"} else "port"
+    what = ("the unmodified numba kernel numbas.invert_standard_2D (oracle/_ref)" if kind == "reference"
+            else "C port of numbas.py (gcc -O2, no FMA)")
     sample = (f"{sweeps} lexicographic sweeps of {nthreads} {nx}x{ny} slice(s) per step, one host process per slice "
-              f"({nthreads} of {os.cpu_count()} cores; the job has {nslices} slices), C port of numbas.py (gcc -O2, no FMA)")
+              f"({nthreads} of {os.cpu_count()} cores; the job has {nslices} slices), {what}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# iterations to tolerance (rank 0, N = 1)
+# ---------------------------------------------------------------------------
+def iters_to_tol(ctx, log):
+    """Sweeps until the reference's stop test fires, three ways, at the same omega and tolerance:
+    the reference's lexicographic order on the CPU, the same order on the GPU (XINV_ORDER_LEX), and the
+    GPU's red-black order; plus how far the converged fields are apart (max |a - b| / max |b|)."""
+    import xinvert_b200 as xb
+    out = {}
+    jobs = [("c1", synthetic.poisson_latlon(180, 360, land=False, noise=0.0), ("fixed", "periodic"), 1.4, 1e-8,
+             "configs[0]: 360x180, fixed/periodic, omega=1.4, tol 1e-8 (SURVEY 8c(6): the reference stops after 2381 sweeps)"),
+            ("c2", make_problem("c2", 0)[0], ("extend", "periodic"), None, 1e-6,
+             "configs[1]: 3600x1800 with land mask, extend/periodic, omega=auto, tol 1e-6")]
+    for name, c, bcs, omega, tol, desc in jobs:
+        kind, mod = cpu_impl(prefer_reference=(name == "c1"))       # C2 on the CPU takes a minute even with the port
+        cc = dict(c, B=np.zeros_like(c["A"]) if kind == "reference" else None)
+        if kind == "reference":
+            run_std2d(mod, dict(cc, S0=c["S0"].copy()), bcs[0], bcs[1], 0, tol, omega=omega)     # JIT
+        t0 = time.perf_counter()
+        S_cpu, f_cpu = run_std2d(mod, cc, bcs[0], bcs[1], 5000, tol, omega=omega)
+        t_cpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        S_lex, f_lex = run_std2d(xb, c, bcs[0], bcs[1], 5000, tol, omega=omega, ordering="lexicographic", ctx=ctx)
+        t_lex = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        S_rb, f_rb = run_std2d(xb, c, bcs[0], bcs[1], 5000, tol, omega=omega, ctx=ctx)
+        t_rb = time.perf_counter() - t0
+        scale = float(np.abs(S_cpu).max())
+        out[name] = {
+            "problem": desc, "omega": float(c["p"]["optArg"] if omega is None else omega), "tolerance": tol,
+            "cpu_lexicographic": int(f_cpu[2]) + 1, "gpu_lexicographic": int(f_lex[2]) + 1, "gpu_redblack": int(f_rb[2]) + 1,
+            "cpu_kind": kind, "cpu_s": t_cpu, "gpu_lexicographic_s": t_lex, "gpu_redblack_s": t_rb,
+            "last_rel_change": {"cpu": float(f_cpu[1]), "gpu_lexicographic": float(f_lex[1]), "gpu_redblack": float(f_rb[1])},
+            "gpu_lexicographic_equals_cpu_bitwise": bool(np.array_equal(S_lex, S_cpu)),
+            "max_rel_field_diff_redblack_vs_lexicographic": float(np.abs(S_rb - S_cpu).max() / scale),
+            "max_abs_psi": scale,
+        }
+        log(f"iters_to_tol {name}: cpu-lex {out[name]['cpu_lexicographic']} gpu-lex {out[name]['gpu_lexicographic']} "
+            f"gpu-rb {out[name]['gpu_redblack']} ({t_cpu:.1f} / {t_lex:.1f} / {t_rb:.2f} s)")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# the other BASELINE configs, sweep-loop rate (rank 0, N = 1)
+# ---------------------------------------------------------------------------
+def secondary_configs(ctx, peak, log):
+    import xinvert_b200 as xb
+    out = {}
+
+    def entry(name, desc, N, batch, sweeps, st, alg_bytes_per_sweep, note):
+        us = st["solve_ms"] * 1e3 / sweeps
+        gbs = (alg_bytes_per_sweep / (us * 1e-6) / 1e9) if alg_bytes_per_sweep else None
+        out[name] = {"workload": desc, "value": sweeps * N * batch / (st["solve_ms"] * 1e-3), "unit": UNIT,
+                     "us_per_sweep": us, "sweeps": sweeps, "engine": st["engine"], "iters_per_pass": st["iters_per_pass"],
+                     "row_coeffs": st["row_coeffs"], "kernel_launches": st["kernel_launches"],
+                     "roofline": {"bound": "hbm" if gbs else "latency", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                  "frac": (gbs / peak) if gbs else None, "alg_bytes_per_sweep": alg_bytes_per_sweep,
+                                  "note": note}}
+        log(f"config {name}: {out[name]['value']:.3e} cell-updates/s, {us:.2f} us/sweep, frac {out[name]['roofline']['frac']}")
+
+    kw = dict(undef=UNDEF, tolerance=-1.0, ctx=ctx)
+    # c1: 360x180 Poisson
+    c, bcs = make_problem("c1", 0)
+    p = c["p"]
+    for _ in range(2):
+        S = c["S0"].copy()
+        _, st = xb.solve_standard_2D(S, c["A"], None, c["C"], c["F"], bcs[0], bcs[1], p["del1Sqr"], p["ratioQtr"], p["ratioSqr"],
+                                     1.4, mxLoop=1999, **kw)
+    entry("c1", WORKLOADS["c1"][4], 180 * 360, 1, 2000, st, None,
+          "0.5 MB per array: L2-resident, bound by the latency of one strip's pipeline and the grid barrier")
+    # c3: invert_omega 360x180x37, 3-D N2
+    c = synthetic.omega_latlon(37, 180, 360, seed=1, n2="3d")
+    p = c["p"]
+    for _ in range(2):
+        S = c["S0"].copy()
+        _, st = xb.solve_standard_3D(S, c["A"], c["B"], c["C"], c["F"], "fixed", "fixed", "periodic", p["del1Sqr"],
+                                     p["ratio2Sqr"], p["ratio1Sqr"], p["optArg"], mxLoop=199, **kw)
+    N3 = 37 * 180 * 360
+    entry("c3", "configs[2]: invert_omega 360x180x37, A = f^2 cos(lat), B and C from a 3-D N^2, fixed/fixed/periodic",
+          N3, 1, 200, st, (40.0 if st["row_coeffs"] else 48.0) * N3,
+          "one red+black iteration per pass; algorithmic bytes = omega r+w, B, C, F (+ A unless constant along x); "
+          "the march is bound by dependent latency per level step (~0.75 us), not by bytes")
+    # c4: invert_GillMatsuno 720x360 beta plane
+    c = synthetic.gill_matsuno_beta(360, 720)
+    p = c["p"]
+    for _ in range(2):
+        S = c["S0"].copy()
+        _, st = xb.solve_general_2D(S, c["A"], None, c["C"], c["D"], c["E"], c["F"], c["G"], "fixed", "periodic", p["del1"],
+                                    p["del1Sqr"], p["ratio"], p["ratioQtr"], p["ratioSqr"], 1.4, mxLoop=999, **kw)
+    entry("c4", "configs[3]: invert_GillMatsuno 720x360 beta plane (phi; u, v follow from cal_flow)", 360 * 720, 1, 1000, st, None,
+          "2 MB per array: L2-resident, latency-bound")
+    # c5: 32 slices of 1440x720 (one GPU's share of configs[4] on 8 GPUs)
+    c, bcs = make_problem("c5", 0)
+    p = c["p"]
+    for _ in range(2):
+        S = c["S0"].copy()
+        _, st = xb.solve_standard_2D(S, c["A"], None, c["C"], c["F"], bcs[0], bcs[1], p["del1Sqr"], p["ratioQtr"], p["ratioSqr"],
+                                     p["optArg"], mxLoop=199, **kw)
+    N5 = 720 * 1440
+    entry("c5", WORKLOADS["c5"][4], N5, 32, 200, st, 24.0 * N5 * 32 / st["iters_per_pass"] if st["row_coeffs"] else 40.0 * N5 * 32 / st["iters_per_pass"],
+          "bytes per sweep = bytes per pass / iterations per pass (psi r+w and F once per pass)")
+    del c, S
+    # the reference's only published timing: notebook 11, invert_omega 601x300x300, N2 a profile along the levels
+    c = synthetic.omega_latlon(300, 300, 602, seed=11, n2="1d", dlev=-10.0, lat0=30.0, dlat=1.0 / 30.0, dlon=1.0 / 60.0)
+    p = c["p"]
+    for _ in range(2):
+        S = c["S0"].copy()
+        _, st = xb.solve_standard_3D(S, c["A"], c["B"], c["C"], c["F"], "fixed", "fixed", "extend", p["del1Sqr"],
+                                     p["ratio2Sqr"], p["ratio1Sqr"], p["optArg"], mxLoop=49, **kw)
+    Nn = 300 * 300 * 602
+    entry("omega_notebook11", "docs/source/notebooks/11_Omega_equation.ipynb:525-551: invert_omega 601x300x300 "
+          "(the reference: ~730 s per 501-sweep solve)", Nn, 1, 50, st, (40.0 if st["row_coeffs"] else 48.0) * Nn,
+          "HBM-bound: algorithmic bytes = omega r+w, B, C, F (+ A unless constant along x)")
+    return out
 
 
 # ---------------------------------------------------------------------------
@@ -248,23 +413,9 @@ def run_ours(args):
     if world > 1:
         allreduce = xd.XinvNcclAllReduce(ctx, rank, world) if args.collective == "xinv-nccl" else xd.TorchAllReduce()
 
-    ny, nx, per_gpu, bcs, desc = WORKLOADS[args.workload]
-    c, _ = make_problem(args.workload, rank, pinned=True)
-    p = c["p"]
-    N = ny * nx
-    sweeps = args.sweeps
-    kw = dict(undef=UNDEF, mxLoop=sweeps - 1, tolerance=-1.0, ctx=ctx, engine=args.engine)
-    if world > 1 or args.chunk != 128:
-        # ranks exchange their active-slice counts (one scalar all-reduce) after every chunk of passes;
-        # ~6 ms of device work per chunk keeps that exchange below 1 % of the step
-        kw["sweeps_per_chunk"] = args.chunk
-    pos = (bcs[0], bcs[1], p["del1Sqr"], p["ratioQtr"], p["ratioSqr"], p["optArg"])
-
-    # ---- device-resident operands (value) --------------------------------
-    dA, dC, dF = (torch.from_numpy(np.ascontiguousarray(c[k])).to(dev) for k in ("A", "C", "F"))
-    dS0 = torch.from_numpy(np.ascontiguousarray(c["S0"])).to(dev)
-    dS = dS0.clone()
-    torch.cuda.synchronize()
+    def log(msg):
+        if rank == 0:
+            print("[bench] " + msg, file=sys.stderr, flush=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -272,103 +423,155 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device(profile=False):
-        dS.copy_(dS0)
-        torch.cuda.synchronize()          # torch stream -> library stream hand-over (a 52 MB memset-like copy)
-        return xd.solve_standard_2D_sharded(dS, dA, None, dC, dF, *pos, allreduce=allreduce, profile=profile, **kw)
+    def measure(workload, sweeps, steps, warmup, slices=None, first_slice=0, with_cabi=True, clocks=None):
+        """Device-resident value, e2e through invert_Poisson and (optionally) through the full-array C-ABI for one
+        workload; every time is the maximum over the ranks."""
+        import datetime
+        ny, nx, per_gpu, bcs, desc = WORKLOADS[workload]
+        if slices is not None:
+            per_gpu = slices
+        c, _ = make_problem(workload, rank, pinned=True, slices=per_gpu)
+        p = c["p"]
+        N = ny * nx
+        kw = dict(undef=UNDEF, mxLoop=sweeps - 1, tolerance=-1.0, ctx=ctx, engine=args.engine)
+        if world > 1 or args.chunk != 128:
+            # ranks exchange their active-slice counts (one scalar all-reduce) after every chunk of passes;
+            # ~6 ms of device work per chunk keeps that exchange below 1 % of the step
+            kw["sweeps_per_chunk"] = args.chunk
+        pos = (bcs[0], bcs[1], p["del1Sqr"], p["ratioQtr"], p["ratioSqr"], p["optArg"])
+        dA, dC, dF = (torch.from_numpy(np.ascontiguousarray(c[k])).to(dev) for k in ("A", "C", "F"))
+        dS0 = torch.from_numpy(np.ascontiguousarray(c["S0"])).to(dev)
+        dS = dS0.clone()
+        torch.cuda.synchronize()
 
-    def step_host(S):
-        # S is in/out: every step gets its own pinned buffer holding the initial guess, prepared
-        # before the timed region, so the region holds the API call (H2D + solve + D2H) and nothing else
-        return xd.solve_standard_2D_sharded(S, c["A"], None, c["C"], c["F"], *pos, allreduce=allreduce, **kw)
+        def step_device(profile=False):
+            dS.copy_(dS0)                  # (the library waits for torch's stream before it reads the operands)
+            return xd.solve_standard_2D_sharded(dS, dA, None, dC, dF, *pos, allreduce=allreduce, profile=profile, **kw)
 
-    import datetime
+        for _ in range(warmup):
+            step_device()
+        barrier()
+        r = {"launches": 0, "solve_ms": 0.0, "dom_ms": 0.0, "dom_n": 0}
+        t0 = time.perf_counter()
+        w0 = datetime.datetime.now()
+        ctx.timer_start()                          # CUDA events on the library's stream bracket the K steps
+        for _ in range(steps):
+            fl, st, _ = step_device(profile=True)
+            r["launches"] += st["kernel_launches"]
+            r["solve_ms"] += st["solve_ms"]
+            r["dom_ms"] += st["dom_ms"]; r["dom_n"] += st["dom_launches"]
+        r["ev_s"] = ctx.timer_stop() / 1e3
+        w1 = datetime.datetime.now()
+        barrier()
+        r["wall"] = time.perf_counter() - t0
+        r["window"] = (w0, w1)
+        assert int(fl[0, 2]) + 1 == sweeps, (fl[0], sweeps)
+        r["st"] = st
+        del dA, dC, dF, dS, dS0
+
+        e2e_steps = max(1, min(steps, 5))
+        r["e2e_steps"] = e2e_steps
+        # ---- end to end through the C-ABI with full host arrays -------------------
+        if with_cabi:
+            hS = []
+            for _ in range(e2e_steps + 1):
+                buf = xb.pinned_empty(c["S0"].shape)
+                buf[...] = c["S0"]
+                hS.append(buf)
+
+            def step_host(S):
+                # S is in/out: every step gets its own pinned buffer holding the initial guess, prepared
+                # before the timed region, so the region holds the API call (H2D + solve + D2H) and nothing else
+                return xd.solve_standard_2D_sharded(S, c["A"], None, c["C"], c["F"], *pos, allreduce=allreduce, **kw)
+
+            step_host(hS[e2e_steps])
+            barrier()
+            ctx.timer_start()
+            for i in range(e2e_steps):
+                _, st_h, _ = step_host(hS[i])
+            r["ev_cabi"] = ctx.timer_stop() / 1e3
+            r["st_cabi"] = st_h
+            barrier()
+            del hS
+        # ---- the call a user makes: invert_Poisson(F) with the forcing in (pinned / pageable) host memory ----
+        nb = per_gpu
+        hz = xb.pinned_empty((nb, ny, nx) if nb > 1 else (ny, nx))
+        for t in range(nb):
+            zeta, lat, lon = synthetic.poisson_latlon_user(ny, nx, land=(workload != "c1"), noise=1e-6,
+                                                           seed=1000 + (first_slice + t), phase=2 * np.pi * (first_slice + t) / max(nb * world, 1))
+            (hz[t] if nb > 1 else hz)[...] = zeta
+        coords = {'lat': lat, 'lon': lon}
+        ipa = {'BCs': list(bcs), 'optArg': p["optArg"], 'mxLoop': sweeps - 1, 'tolerance': -1.0, 'printInfo': False,
+               'ctx': ctx, 'engine': args.engine}
+
+        def api_run(values, nsteps):
+            Fda = (xb.DataArray(values, ['time', 'lat', 'lon'], dict(coords, time=np.arange(nb))) if nb > 1
+                   else xb.DataArray(values, ['lat', 'lon'], coords))
+            xb.invert_Poisson(Fda, dims=['lat', 'lon'], iParams=dict(ipa))
+            barrier()
+            ctx.timer_start()
+            for _ in range(nsteps):
+                xb.invert_Poisson(Fda, dims=['lat', 'lon'], iParams=dict(ipa))
+            ev = ctx.timer_stop() / 1e3
+            st_a = ctx.stats()
+            barrier()
+            return ev, st_a
+
+        r["ev_api"], st_a = api_run(hz, e2e_steps)
+        assert st_a["sweeps_launched"] * st_a["iters_per_pass"] >= sweeps
+        r["st_api"] = st_a
+        pg_steps = max(1, min(e2e_steps, 2))
+        r["ev_api_pageable"], r["st_api_pageable"] = api_run(np.array(hz, copy=True), pg_steps)   # ordinary (pageable) numpy memory
+        r["pg_steps"] = pg_steps
+        # ---- reduce over ranks: device time of the timed region = max over ranks ----
+        keys = ["ev_s", "wall", "ev_api", "ev_api_pageable"] + (["ev_cabi"] if with_cabi else [])
+        vals = torch.tensor([r[k] for k in keys] + [r["solve_ms"] / 1e3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        for k, v in zip(keys + ["t_dev"], vals.tolist()):
+            r[k] = float(v)
+        tl = torch.tensor([r["launches"]], dtype=torch.int64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tl)
+        r["launches"] = int(tl.item())
+        r.update(N=N, per_gpu=per_gpu, bcs=bcs, desc=desc, sweeps=sweeps, steps=steps)
+        return r
+
+    import datetime  # noqa: F401
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    launches = 0
-    solve_ms = 0.0
-    dom_ms, dom_n = 0.0, 0
-    t0 = time.perf_counter()
-    w0 = datetime.datetime.now()
-    ctx.timer_start()                          # CUDA events on the library's stream bracket the K steps
-    for _ in range(args.steps):
-        fl, st, _ = step_device(profile=True)
-        launches += st["kernel_launches"]
-        solve_ms += st["solve_ms"]
-        dom_ms += st["dom_ms"]; dom_n += st["dom_launches"]
-    ev_s = ctx.timer_stop() / 1e3
-    w1 = datetime.datetime.now()
-    barrier()
-    wall = time.perf_counter() - t0
-    assert int(fl[0, 2]) + 1 == sweeps, (fl[0], sweeps)
-    engine_used, ncol = st["engine"], st["ncolours"]
+    sweeps = args.sweeps
+    m = measure(args.workload, sweeps, args.steps, args.warmup)
+    clk = clocks.stop(m["window"]) if rank == 0 else None
+    log(f"headline {args.workload}: {sweeps * m['N'] * m['per_gpu'] * world * args.steps / m['ev_s']:.3e} cell-updates/s")
 
-    # ---- end to end through the C-ABI with host buffers ---------------------
-    e2e_steps = max(1, min(args.steps, 5))
-    hS = []
-    for _ in range(e2e_steps + 1):
-        buf = xb.pinned_empty(c["S0"].shape)
-        buf[...] = c["S0"]
-        hS.append(buf)
-    step_host(hS[e2e_steps])
-    barrier()
-    t1 = time.perf_counter()
-    ctx.timer_start()
-    h2d = d2h = 0
-    for i in range(e2e_steps):
-        _, st_h, _ = step_host(hS[i])
-        h2d, d2h = st_h["h2d_bytes"], st_h["d2h_bytes"]
-    ev_e2e = ctx.timer_stop() / 1e3
-    barrier()
-    wall_e2e = time.perf_counter() - t1
-    clk = clocks.stop((w0, w1)) if rank == 0 else None
+    # ---- N > 1: BASELINE configs[4] exactly (256 slices cut over the ranks) ----
+    c4x = None
+    if world > 1 and not args.no_extras:
+        lo, hi = xd.shard_bounds(C5_TOTAL_SLICES, world, rank)
+        m5 = measure("c5", 200, 2, 1, slices=hi - lo, first_slice=lo, with_cabi=False)
+        units5 = 200 * m5["N"] * C5_TOTAL_SLICES
+        c4x = {"workload": f"configs[4]: batched invert_Poisson 1440x720 x {C5_TOTAL_SLICES} time slices sharded over {world} GPUs "
+                           f"(distributed.shard_bounds: {hi - lo} slices on rank 0)",
+               "value": units5 * m5["steps"] / m5["ev_s"], "unit": UNIT, "sweeps_per_step": 200, "steps": m5["steps"],
+               "ms_per_step": 1e3 * m5["ev_s"] / m5["steps"],
+               "e2e": {"value": units5 * m5["e2e_steps"] / m5["ev_api"], "unit": UNIT,
+                       "h2d_bytes_per_step": int(m5["st_api"]["h2d_bytes"]), "d2h_bytes_per_step": int(m5["st_api"]["d2h_bytes"]),
+                       "h2d_ms": m5["st_api"]["h2d_ms"], "d2h_ms": m5["st_api"]["d2h_ms"], "ms_per_step": 1e3 * m5["ev_api"] / m5["e2e_steps"]},
+               "e2e_pageable": {"value": units5 * m5["pg_steps"] / m5["ev_api_pageable"], "unit": UNIT}}
 
-    # ---- the call a user makes: invert_Poisson(F) with the forcing in (pinned) host memory ----------
-    from tests import cases
-    nb = per_gpu
-    hz = xb.pinned_empty((nb, ny, nx) if nb > 1 else (ny, nx))
-    for t in range(nb):
-        zeta, lat, lon = cases.poisson_latlon_user(ny, nx, land=(args.workload != "c1"), noise=1e-6,
-                                                   seed=1000 + rank * nb + t, phase=0.37 * rank + 2 * np.pi * t / nb)
-        (hz[t] if nb > 1 else hz)[...] = zeta
-    coords = {'lat': lat, 'lon': lon}
-    Fda = (xb.DataArray(hz, ['time', 'lat', 'lon'], dict(coords, time=np.arange(nb))) if nb > 1
-           else xb.DataArray(hz, ['lat', 'lon'], coords))
-    ipa = {'BCs': list(bcs), 'optArg': p["optArg"], 'mxLoop': sweeps - 1, 'tolerance': -1.0, 'printInfo': False,
-           'ctx': ctx, 'engine': args.engine}
-    xb.invert_Poisson(Fda, dims=['lat', 'lon'], iParams=dict(ipa))
-    barrier()
-    ctx.timer_start()
-    for _ in range(e2e_steps):
-        xb.invert_Poisson(Fda, dims=['lat', 'lon'], iParams=dict(ipa))
-    ev_api = ctx.timer_stop() / 1e3
-    st_a = ctx.stats()
-    assert st_a["sweeps_launched"] * st_a["iters_per_pass"] >= sweeps
-    api = {"ev_s": ev_api, "h2d": st_a["h2d_bytes"], "d2h": st_a["d2h_bytes"], "h2d_ms": st_a["h2d_ms"],
-           "d2h_ms": st_a["d2h_ms"]}
-    barrier()
-
-    # ---- reduce over ranks: device time of the timed region = max over ranks ----
-    t_dev = solve_ms / 1e3
-    vals = torch.tensor([t_dev, wall, wall_e2e, ev_s, ev_e2e, api["ev_s"]], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    t_dev, wall, wall_e2e, ev_s, ev_e2e, ev_api = (float(v) for v in vals.tolist())
-    tot_launch = torch.tensor([launches], dtype=torch.int64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tot_launch)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
+    N, per_gpu, st = m["N"], m["per_gpu"], m["st"]
+    ny, nx = WORKLOADS[args.workload][0], WORKLOADS[args.workload][1]
+    engine_used, ncol = st["engine"], st["ncolours"]
     units_per_step = sweeps * N * per_gpu * world
-    value = units_per_step * args.steps / ev_s             # CUDA-event time, max over ranks
-    e2e_value = units_per_step * e2e_steps / ev_e2e
+    value = units_per_step * args.steps / m["ev_s"]             # CUDA-event time, max over ranks
+    e2e_steps = m["e2e_steps"]
 
     # ---- roofline of the dominant kernel (SURVEY.md 8d algorithmic bytes) ----
     peaks = {}
@@ -378,13 +581,14 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
+    dom_ms, dom_n = m["dom_ms"], m["dom_n"]
     if engine_used == "fused" and st["row_coeffs"]:
         # A and C are constant along x here (lat-lon Poisson): the kernel moves psi r+w and F only,
         # so only those bytes are claimed (SURVEY.md 8d rule: never claim bytes that were not needed)
         alg_bytes = 24.0 * N * per_gpu
         kern = f"fused kernel, {st['iters_per_pass']} red+black iterations per pass, row coefficients (psi r+w, F)"
-        limiter = ("FP64 issue: per ncu (profiles/r01_v3_fused_rc_ncu_full.txt) the FP64 pipe is 48 % busy, issue slots "
-                   "63 %, DRAM 38 %; 68 of 167 warp-instructions per row step are FP64 and hold the pipe 2 cycles each")
+        limiter = ("FP64 issue: per the committed ncu capture (profiles/traffic.json names it) the FP64 pipe and the issue "
+                   "slots are the busiest units, DRAM is under 40 % busy")
     elif engine_used == "fused":
         alg_bytes = 40.0 * N * per_gpu          # one pass: S r+w, A, C, F once
         kern = f"fused kernel, {st['iters_per_pass']} red+black iterations per pass (psi r+w, A, C, F)"
@@ -396,49 +600,68 @@ def run_ours(args):
     achieved = (alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9) if dom_n else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel from the committed
     # `ncu --set full` capture (profiles/traffic.json; C2 workload, one slice per GPU)
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = ("fused_rc" if st["row_coeffs"] else "fused_general") if engine_used == "fused" else "colour"
         if args.workload == "c2":
             traffic = tj[key]["dram_bytes_per_launch"]
+            traffic_src = tj[key].get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": kern, "limiter": limiter, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "avg_launch_us": (dom_ms / dom_n * 1e3) if dom_n else None, "timed_launches": dom_n}
 
     # ---- CPU baseline: bounded sample of the same workload on one host core ----
     cpu_sweeps = args.cpu_sweeps or max(2, int(round(1.2e9 / N)))             # ~10-20 s of CPU work
-    cpu_rate, cpu_dt = cpu_reference_rate(args.workload, cpu_sweeps)
-    cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
+    cpu_kind, cpu_rate, cpu_dt = cpu_reference_rate(args.workload, cpu_sweeps)
+    cpu_what = ("the unmodified numba kernel numbas.invert_standard_2D (oracle/_ref, JIT excluded)" if cpu_kind == "reference"
+                else "C port of numbas.py")
+    cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                     "sample": f"{cpu_sweeps} lexicographic sweeps of one {nx}x{ny} slice ({cpu_dt:.1f} s), "
-                              "C port of numbas.py, 1 thread (the reference is single-threaded)"}
+                              f"{cpu_what}, 1 thread (the reference is single-threaded)"}
 
+    api, cabi = m["st_api"], m.get("st_cabi")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * m["ev_s"] / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "sweeps_per_step": sweeps,
+        "config": {"workload": f"{args.workload}: {m['desc']}", "sweeps_per_step": sweeps,
                    "slices_per_gpu": per_gpu, "grid": [ny, nx], "engine": engine_used, "colours": ncol,
                    "ordering": "red-black", "l2": f"operands {5 * 8 * N * per_gpu / 1e6:.0f} MB per GPU "
                    + ("> 126 MB L2 (no flush needed)" if 40 * N * per_gpu > 126e6 else "< L2: L2-resident workload"),
                    "collective": (args.collective if world > 1 else "none"),
-                   "sweep_loop_ms_per_step": 1e3 * t_dev / args.steps,
-                   "wall_ms_per_step": 1e3 * wall / args.steps},
+                   "sweep_loop_ms_per_step": 1e3 * m["t_dev"] / args.steps,
+                   "wall_ms_per_step": 1e3 * m["wall"] / args.steps},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "e2e": {"value": units_per_step * e2e_steps / ev_api, "unit": UNIT, "h2d_bytes_per_step": int(api["h2d"]),
-                "d2h_bytes_per_step": int(api["d2h"]), "steps": e2e_steps, "ms_per_step": 1e3 * ev_api / e2e_steps,
+        "e2e": {"value": units_per_step * e2e_steps / m["ev_api"], "unit": UNIT, "h2d_bytes_per_step": int(api["h2d_bytes"]),
+                "d2h_bytes_per_step": int(api["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": 1e3 * m["ev_api"] / e2e_steps,
                 "h2d_ms": api["h2d_ms"], "d2h_ms": api["d2h_ms"],
                 "call": "xinvert_b200.invert_Poisson(F, dims, iParams): forcing in pinned host memory, "
                         "C-ABI xinv_std2d_rows underneath"},
-        "e2e_cabi": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                     "steps": e2e_steps, "ms_per_step": 1e3 * ev_e2e / e2e_steps,
-                     "h2d_ms": st_h["h2d_ms"], "d2h_ms": st_h["d2h_ms"],
+        "e2e_pageable": {"value": units_per_step * m["pg_steps"] / m["ev_api_pageable"], "unit": UNIT, "steps": m["pg_steps"],
+                         "ms_per_step": 1e3 * m["ev_api_pageable"] / m["pg_steps"],
+                         "h2d_ms": m["st_api_pageable"]["h2d_ms"], "d2h_ms": m["st_api_pageable"]["d2h_ms"],
+                         "call": "the same call with the forcing in ordinary (pageable) numpy memory"},
+        "e2e_cabi": {"value": units_per_step * e2e_steps / m["ev_cabi"], "unit": UNIT, "h2d_bytes_per_step": int(cabi["h2d_bytes"]),
+                     "d2h_bytes_per_step": int(cabi["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": 1e3 * m["ev_cabi"] / e2e_steps,
+                     "h2d_ms": cabi["h2d_ms"], "d2h_ms": cabi["d2h_ms"],
                      "call": "C-ABI xinv_std2d (the reference's core.inv_standard2D boundary): full S, A, C, F host arrays"},
-        "gpu_launches": int(tot_launch.item()), "clocks": clk,
+        "gpu_launches": m["launches"], "clocks": clk,
     }
+    if c4x is not None:
+        line["configs4"] = c4x
+    if world == 1 and not args.no_extras:
+        try:
+            line["iters_to_tol"] = iters_to_tol(ctx, log)
+        except Exception as e:                       # the headline must not be lost to a secondary measurement
+            line["iters_to_tol"] = {"error": repr(e)}
+        try:
+            line["configs"] = secondary_configs(ctx, peak, log)
+        except Exception as e:
+            line["configs"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -457,6 +680,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=128, help="passes between two scalar all-reduces (multi-GPU runs)")
     ap.add_argument("--cpu-sweeps", type=int, default=0, help="sweeps of the cpu_baseline sample (0 = ~10-20 s)")
     ap.add_argument("--ref-sweeps", type=int, default=0, help="sweeps per step of --impl reference (0 = ~2-3 s)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline only: skip iters_to_tol / configs (N = 1) and configs4 (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -7,61 +7,8 @@ operand of the stencils.
 """
 import numpy as np
 
-UNDEF = -9.99e8
-REARTH = 6371200.0
-
-
-def params2d(ny, nx, del2, del1):
-    """numpy restatement of apps.__cal_params2D (apps.py:2282-2291)."""
-    ratio = del1 / del2
-    eps = np.sin(np.pi / (2.0 * nx + 2.0)) ** 2 + np.sin(np.pi / (2.0 * ny + 2.0)) ** 2
-    return dict(gc2=ny, gc1=nx, del2=del2, del1=del1, ratio=ratio, ratioSqr=ratio ** 2.0,
-                ratioQtr=ratio / 4.0, del1Sqr=del1 ** 2.0,
-                optArg=2.0 / (1.0 + np.sqrt((2.0 - eps) * eps)))
-
-
-def poisson_latlon(ny, nx, land=True, noise=1e-6, seed=0, batch=None, phase=0.0):
-    """lat-lon Poisson problem: A=cosH, C=1/cosG, F=zeta*cosG with an optional
-    land mask (apps.py:1401-1409); zeta is the SURVEY.md 8d formula."""
-    dlat, dlon = 180.0 / ny, 360.0 / nx
-    lat = -90.0 + dlat / 2 + dlat * np.arange(ny)
-    lon = dlon * np.arange(nx)
-    lats = np.deg2rad(lat)
-    cosG = np.cos(lats)
-    latm = np.empty(ny)
-    latm[0] = np.nan
-    latm[1:] = lats[:-1]
-    cosH = np.cos((lats + latm) / 2.0)
-    lam = np.deg2rad(lon)[None, :]
-    phi = lats[:, None]
-    rng = np.random.default_rng(seed)
-    shape = (ny, nx) if batch is None else (batch, ny, nx)
-    ph = phase if batch is None else (2 * np.pi * np.arange(batch) / batch)[:, None, None]
-    zeta = 1e-5 * np.sin(3 * lam + ph) * np.cos(phi) ** 2 * np.sin(2 * phi)
-    zeta = np.broadcast_to(zeta, shape) + noise * rng.standard_normal(shape)
-    zeta = np.ascontiguousarray(zeta)
-    F = zeta * cosG[:, None]
-    if land:
-        mask = np.sin(5 * lam) * np.cos(3 * phi) > 0.6
-        F[..., mask] = UNDEF
-    A = np.ascontiguousarray(np.broadcast_to(cosH[:, None], (ny, nx)))
-    C = np.ascontiguousarray(np.broadcast_to(1.0 / cosG[:, None], (ny, nx)))
-    p = params2d(ny, nx, np.deg2rad(dlat) * REARTH, np.deg2rad(dlon) * REARTH)
-    return dict(A=A, C=C, F=F, p=p, S0=np.zeros(shape))
-
-
-def poisson_latlon_user(ny, nx, land=True, noise=1e-6, seed=0, phase=0.0):
-    """The same problem as poisson_latlon the way a user of invert_Poisson holds it: the raw
-    vorticity (NaN on land) and the lat / lon coordinates."""
-    dlat, dlon = 180.0 / ny, 360.0 / nx
-    lat = -90.0 + dlat / 2 + dlat * np.arange(ny)
-    lon = dlon * np.arange(nx)
-    lam, phi = np.deg2rad(lon)[None, :], np.deg2rad(lat)[:, None]
-    rng = np.random.default_rng(seed)
-    zeta = 1e-5 * np.sin(3 * lam + phase) * np.cos(phi) ** 2 * np.sin(2 * phi) + noise * rng.standard_normal((ny, nx))
-    if land:
-        zeta[np.sin(5 * lam) * np.cos(3 * phi) > 0.6] = np.nan
-    return zeta, lat, lon
+from synthetic import (REARTH, UNDEF, gill_matsuno_beta, omega_latlon, params2d, params3d,  # noqa: F401
+                       poisson_latlon, poisson_latlon_user)
 
 
 def random_std2d(ny, nx, with_B, seed, land=0.1, batch=None):

@@ -27,8 +27,14 @@ def test_reference_arm_json_line():
     assert d["value"] > 1e6 and d["e2e"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "sample" in cb
+    # "reference" where oracle/_ref (or /root/reference) holds the unmodified numba kernels, else the C port
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["config"]["workload"].startswith("c1") and d["dtype"] == "f64" and d["scaling"] == "weak"
+
+
+def test_reference_arm_falls_back_to_the_port():
+    d = json.loads(_run({"XINV_BENCH_CPU": "port"}))
+    assert d["cpu_baseline"]["kind"] == "port"
 
 
 def test_reference_arm_multi_rank_only_rank0_prints_and_uses_one_process_per_slice():
