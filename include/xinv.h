@@ -168,6 +168,23 @@ int xinv_gen2d_rows(xinv_ctx *ctx, double *S_out, const double *rows, const doub
                     double optArg, double undef, double *flags,
                     int64_t mxLoop, double tolerance, const xinv_opts *opts);
 
+/* The same front end for invert_omega (apps.py:766-827, :2016-2052): rows = [4][ny]:
+ *   rows[0] = A of every row (lat-lon: f^2 cos(lat); cartesian: f^2), the same on every level;
+ *   rows[1] = the factor of B = N2 * rows[1] (cosH | 1);  rows[2] = the divisor of C = N2 / rows[2] (cosG | 1);
+ *   rows[3] = the forcing scale (cosG | 1).
+ * N2 is read as N2[b*n2_strides[0] + k*n2_strides[1] + j*n2_strides[2] + i*n2_strides[3]] (elements; 0 =
+ * broadcast): a scalar, a profile along one core dimension, one volume shared by the batch or a full array;
+ * n2_count = elements in the buffer.  F_user: the user's forcing [batch][nz][ny][nx] (user_undef / NaN = land);
+ * S_out is output only (zero initial guess), land is set to out_undef.  Needs the 3-D fused engine
+ * (even nx when periodic-x): otherwise XINV_E_UNSUPPORTED and the caller falls back to xinv_std3d. */
+int xinv_std3d_rows(xinv_ctx *ctx, double *S_out, const double *rows, const double *N2,
+                    const int64_t *n2_strides, int64_t n2_count, const double *F_user,
+                    double user_undef, double out_undef,
+                    int64_t batch, int64_t nz, int64_t ny, int64_t nx, int bcz, int bcy, int bcx,
+                    double delxSqr, double ratio2Sqr, double ratio1Sqr,
+                    double optArg, double undef, double *flags,
+                    int64_t mxLoop, double tolerance, const xinv_opts *opts);
+
 /* Replaces core.inv_general2D -> numbas.invert_general_2D
  * (core.py:418-428, numbas.py:987-1201).  B == NULL means B == 0. */
 int xinv_gen2d(xinv_ctx *ctx, double *S, const double *A, const double *B,

@@ -136,6 +136,61 @@ def bridge_fourcolour_std2d(ref, c, bcx, iters, omega):
     return S
 
 
+def extend_rows_numpy(P, bcx):
+    """The y-'extend' copy of numbas.py:284-310 / :87-115 on one 2-D level, in numpy: row 0 takes row 1 and
+    row -1 takes row -2 wherever the source is not undef; without periodic-x the corner cells copy their
+    diagonal neighbour."""
+    ny, nx = P.shape
+    cols = np.arange(nx) if bcx == "periodic" else np.arange(1, nx - 1)
+    r1, rm2 = P[1].copy(), P[-2].copy()
+    for dst, src in ((0, r1), (ny - 1, rm2)):
+        ok = src[cols] != UNDEF
+        P[dst, cols[ok]] = src[cols[ok]]
+        if bcx != "periodic":
+            if src[1] != UNDEF:
+                P[dst, 0] = src[1]
+            if src[-2] != UNDEF:
+                P[dst, -1] = src[-2]
+
+
+def bridge_redblack_std2d_extend(ref, c, bcx, iters, omega):
+    """BCy = 'extend' through the bridge: the reference's row copy runs at every CALL, i.e. it would run
+    before each half-sweep; here it is applied once per iteration in numpy (its own statement, no arithmetic)
+    and the reference is called with BCy = 'fixed' (last paragraph)."""
+    p = c["p"]
+    ny, nx = c["F"].shape
+    jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    S = c["S0"].copy()
+    B = _zeros_like_B(c)
+    for _ in range(iters):
+        extend_rows_numpy(S, bcx)
+        for colour in (0, 1):
+            Fm = c["F"].copy()
+            Fm[((ii + jj) & 1) != colour] = UNDEF
+            fl = np.array([0.0, 1.0, 0.0])
+            ref.invert_standard_2D(S, c["A"], B, c["C"], Fm, ny, nx, p["del2"], p["del1"], "fixed", bcx,
+                                   p["del1Sqr"], p["ratioQtr"], p["ratioSqr"], omega, UNDEF, fl, 0, -1.0)
+    return S
+
+
+def bridge_redblack_std3d_extend(ref, c, bcx, iters, omega):
+    p = c["p"]
+    nz, ny, nx = c["F"].shape
+    kk, jj, ii = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    S = c["S0"].copy()
+    for _ in range(iters):
+        for k in range(1, nz - 1):                    # numbas.py:87-115: levels 1..zc-2 only
+            extend_rows_numpy(S[k], bcx)
+        for colour in (0, 1):
+            Fm = c["F"].copy()
+            Fm[((ii + jj + kk) & 1) != colour] = UNDEF
+            fl = np.array([0.0, 1.0, 0.0])
+            ref.invert_standard_3D(S, c["A"], c["B"], c["C"], Fm, nz, ny, nx, p["del3"], p["del2"], p["del1"],
+                                   "fixed", "fixed", bcx, p["del1Sqr"], p["ratio2Sqr"], p["ratio1Sqr"], omega,
+                                   UNDEF, fl, 0, -1.0)
+    return S
+
+
 def _pack(c):
     d = {k: v for k, v in c.items() if isinstance(v, np.ndarray)}
     for k, v in c["p"].items():
@@ -209,7 +264,22 @@ def main():
     for bcx in ("fixed", "periodic"):
         out["bridge_std2d_9pt"][f"S_{bcx}"] = bridge_fourcolour_std2d(ref, c, bcx, 5, 1.2)
 
+    # ---- bridge with BCy = 'extend' (row copy applied outside the calls), grids of several strips / tiles ----
+    c = cases.random_std2d(40, 70, with_B=False, seed=151)
+    c["S0"][1, 5:9] = UNDEF                           # sources the copy must skip
+    out["bridge_std2d_extend"] = _pack(c)
+    for bcx in ("fixed", "periodic"):
+        out["bridge_std2d_extend"][f"S_{bcx}"] = bridge_redblack_std2d_extend(ref, c, bcx, 6, 1.4)
+    c = cases.random_std3d(6, 18, 68, seed=152)
+    c["S0"][2, -2, 20:24] = UNDEF
+    out["bridge_std3d_extend"] = _pack(c)
+    for bcx in ("fixed", "periodic"):
+        out["bridge_std3d_extend"][f"S_{bcx}"] = bridge_redblack_std3d_extend(ref, c, bcx, 5, 1.3)
+
+    only = set(sys.argv[1:])
     for tag, d in out.items():
+        if only and tag not in only:
+            continue
         path = os.path.join(HERE, tag + ".npz")
         np.savez_compressed(path, **d)
         print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB, {len(d)} arrays")

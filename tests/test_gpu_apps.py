@@ -339,3 +339,54 @@ def test_general_form_device_front_end_equals_host_path(gpu_ctx, monkeypatch, mo
         lv = s_f.values[:, land]
         assert np.isnan(lv).all() if np.isnan(undef) else (lv == undef).all()
         assert np.isfinite(s_f.values[:, ~land]).all() and np.abs(s_f.values[:, ~land]).max() > 0
+
+
+@pytest.mark.parametrize("n2kind", ["scalar", "profile_lev", "profile_lat", "volume", "full"])
+@pytest.mark.parametrize("coords,bcs", [("lat-lon", ["fixed", "fixed", "periodic"]), ("lat-lon", ["fixed", "extend", "periodic"]),
+                                        ("cartesian", ["fixed", "fixed", "fixed"])])
+def test_omega_device_front_end_equals_host_path(gpu_ctx, monkeypatch, n2kind, coords, bcs):
+    """invert_omega with icbc=None goes through xinv_std3d_rows (masking, A / B = N2*cosH / C = N2/cosG, forcing
+    scale and de-masking on the device, N2 read through strides); the reference-shaped host path must give the same
+    bits: every form of N2 the reference accepts, NaN-marked land, a batch over time."""
+    from xinvert_b200 import apps
+    nz, ny, nx, T = 9, 30, 64, 2
+    lev = 100000.0 - 10000.0 * np.arange(nz)
+    lat, lon = -58.0 + 4.0 * np.arange(ny), 5.625 * np.arange(nx)
+    if coords == "cartesian":
+        lat, lon = 1e5 * np.arange(ny) - 1.4e6, 1e5 * np.arange(nx)
+    rng = np.random.default_rng(5)
+    co = {'time': np.arange(T), 'LEV': lev, 'lat': lat, 'lon': lon}
+    Fv = 1e-17 * rng.standard_normal((T, nz, ny, nx))
+    Fv[:, 2:5, 8:12, 10:20] = np.nan                               # topography
+    F = DA(Fv, ['time', 'LEV', 'lat', 'lon'], co)
+    N2 = {"scalar": 2e-4,
+          "profile_lev": DA(1e-6 * (1 + 0.5 * rng.random(nz)), ['LEV'], {'LEV': lev}),
+          "profile_lat": DA(1e-6 * (1 + 0.5 * rng.random(ny)), ['lat'], {'lat': lat}),
+          "volume": DA(1e-6 * (1 + 0.5 * rng.random((nz, ny, nx))), ['LEV', 'lat', 'lon'], {k: co[k] for k in ('LEV', 'lat', 'lon')}),
+          "full": DA(1e-6 * (1 + 0.5 * rng.random((T, nz, ny, nx))), ['time', 'LEV', 'lat', 'lon'], co)}[n2kind]
+    ip = {'BCs': bcs, 'tolerance': 1e-9, 'mxLoop': 40, 'printInfo': False}
+    kw = dict(dims=['LEV', 'lat', 'lon'], coords=coords, mParams={'N2': N2, 'f0': 1e-4, 'beta': 2e-11})
+    calls = []
+    real = apps._device_solvers.solve_standard_3D_rows
+    monkeypatch.setattr(apps._device_solvers, "solve_standard_3D_rows", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    ip_f = dict(ip)
+    w_f = xb.invert_omega(F, iParams=ip_f, **kw)
+    assert calls, "the device front end was not used"
+    assert gpu_ctx.stats()["engine"] == "fused" and gpu_ctx.stats()["row_coeffs"] == 1
+    monkeypatch.setattr(apps, "_omega_device_front", lambda *a, **k: None)
+    ip_h = dict(ip)
+    w_h = xb.invert_omega(F, iParams=ip_h, **kw)
+    assert np.array_equal(w_f.values, w_h.values, equal_nan=True)
+    assert np.array_equal(ip_f['flags_all'], ip_h['flags_all'])
+    assert np.isnan(w_f.values[:, 2:5, 8:12, 10:20]).all() and np.isfinite(w_f.values[:, 0]).all()
+    assert np.abs(np.nan_to_num(w_f.values)).max() > 0
+
+
+def test_omega_device_front_end_falls_back(gpu_ctx):
+    """Odd nx with periodic-x is not a problem for the fused engine: the call still succeeds (host path, colour engine)."""
+    nz, ny, nx = 6, 20, 31
+    co = {'LEV': 100000.0 - 10000.0 * np.arange(nz), 'lat': -38.0 + 4.0 * np.arange(ny), 'lon': 360.0 / nx * np.arange(nx)}
+    F = DA(1e-17 * np.random.default_rng(1).standard_normal((nz, ny, nx)), ['LEV', 'lat', 'lon'], co)
+    ip = {'BCs': ['fixed', 'fixed', 'periodic'], 'tolerance': -1.0, 'mxLoop': 5, 'printInfo': False}
+    w = xb.invert_omega(F, dims=['LEV', 'lat', 'lon'], iParams=ip, mParams={'N2': 2e-4})
+    assert gpu_ctx.stats()["engine"] == "colour" and np.isfinite(w.values).all()

@@ -99,3 +99,28 @@ def test_fourcolour_std2d_bridge_golden(gpu_ctx, bcx):
     c, out = golden_io.load("bridge_std2d_9pt")
     S, _ = cases.run_std2d(xb, c, "fixed", bcx, 4, -1.0, omega=1.2)
     assert np.array_equal(S, out[f"S_{bcx}"])
+
+
+# ---- the bridge with BCy = 'extend' (row copy applied outside the reference calls), several strips / tiles ----
+@pytest.mark.parametrize("engine", ["colour", "fused"])
+@pytest.mark.parametrize("bcx", ["fixed", "periodic"])
+def test_redblack_std2d_extend_bridge_golden(gpu_ctx, bcx, engine):
+    c, out = golden_io.load("bridge_std2d_extend")
+    S, _ = cases.run_std2d(xb, c, "extend", bcx, 5, -1.0, omega=1.4, engine=engine)
+    assert np.array_equal(S, out[f"S_{bcx}"])
+
+
+@pytest.mark.parametrize("engine", ["colour", "fused"])
+@pytest.mark.parametrize("bcx", ["fixed", "periodic"])
+def test_redblack_std3d_extend_bridge_golden(gpu_ctx, bcx, engine):
+    c, out = golden_io.load("bridge_std3d_extend")
+    S, _ = cases.run_std3d(xb, c, "extend", bcx, 4, -1.0, omega=1.3, engine=engine)
+    assert np.array_equal(S, out[f"S_{bcx}"])
+
+
+@pytest.mark.parametrize("engine", ["colour", "fused"])
+@pytest.mark.parametrize("bcx", ["fixed", "periodic"])
+def test_redblack_std3d_bridge_golden_both_engines(gpu_ctx, bcx, engine):
+    c, out = golden_io.load("bridge_std3d")
+    S, _ = cases.run_std3d(xb, c, "fixed", bcx, 4, -1.0, omega=1.3, engine=engine)
+    assert np.array_equal(S, out[f"S_{bcx}"])

@@ -50,6 +50,7 @@ _STD2D = [_vp] * 6 + [_i64, _i64, _i64, _int, _int] + [_dbl] * 5 + [_vp, _i64, _
 _GEN2D = [_vp] * 9 + [_i64, _i64, _i64, _int, _int] + [_dbl] * 7 + [_vp, _i64, _dbl, _P(XinvOpts)]
 _STD2D_ROWS = [_vp] * 6 + [_dbl, _dbl, _i64, _i64, _i64, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
 _GEN2D_ROWS = [_vp] * 4 + [_int, _dbl, _dbl, _dbl, _dbl, _i64, _i64, _i64, _int, _int] + [_dbl] * 7 + [_vp, _i64, _dbl, _P(XinvOpts)]
+_STD3D_ROWS = [_vp] * 5 + [_i64, _vp, _dbl, _dbl, _i64, _i64, _i64, _i64, _int, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
 _STD3D = [_vp] * 6 + [_i64, _i64, _i64, _i64, _int, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
 SYMBOLS = [
     ("xinv_create", _int, [_P(_vp), _int]),
@@ -71,6 +72,7 @@ SYMBOLS = [
     ("xinv_std2d", _int, _STD2D),
     ("xinv_std2d_rows", _int, _STD2D_ROWS),
     ("xinv_gen2d_rows", _int, _GEN2D_ROWS),
+    ("xinv_std3d_rows", _int, _STD3D_ROWS),
     ("xinv_gen2d", _int, _GEN2D),
     ("xinv_std3d", _int, _STD3D),
     ("xinv_std2d_begin", _int, _STD2D),

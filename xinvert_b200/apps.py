@@ -130,6 +130,9 @@ def invert_omega(F, dims, coords='lat-lon', icbc=None,
             raise Exception('nan in coefficient A')
         if (v <= 0).any():
             raise Exception('unstable stratification in coefficient A')
+    fast = _omega_device_front(F, dims, coords, icbc, mParams, iParams)
+    if fast is not None:
+        return fast
     return _template(_coeffs_omega, core.inv_standard3D, 3, F, dims, coords,
                      icbc, ['f0', 'beta', 'N2', 'g', 'Omega', 'Rearth'],
                      mParams, iParams)
@@ -551,6 +554,70 @@ def _general_device_front(rows_func, valid, F, dims, coords, icbc, mParams, iPar
             g.values, rows, r['g_mode'], r['g_p1'], r['g_p2'], ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1],
             ip['del1'], ip['del1Sqr'], ip['ratio'], ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp,
             ip['flags'], ip['mxLoop'], ip['tolerance'], ctx=ip.get('ctx'))
+    except XinvError as e:
+        if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
+            return None
+        raise
+    _, noncore, _ = core._layout(F, dims)
+    core._report(ip, core._slice_labels(F, noncore), flags)
+    _report_flags(iParams, flags)
+    return wrap_like(F, S, name='inverted')
+
+
+def _omega_device_front(F, dims, coords, icbc, mParams, iParams):
+    """invert_omega through the device-side front end (``xinv_std3d_rows``), or None when the reference-shaped
+    host path has to be taken (see _poisson_device_front).  A, the factor of B, the divisor of C and the forcing
+    scale are vectors along the second core dim; N2 (scalar, profile, volume or full array) is handed over as it
+    is and read through strides."""
+    if icbc is not None or len(dims) != 3:
+        return None
+    ip = _update(default_iParams, iParams)
+    if ip.get('ordering', 'colour') not in ('colour', 'color', 'redblack', 'red-black') or \
+            ip.get('engine', 'auto') == 'colour' or core.solvers is not _device_solvers:
+        return None
+    mp = _update(default_mParams, mParams, ['f0', 'beta', 'N2', 'g', 'Omega', 'Rearth'])
+    g = _Grid(F, dims)
+    if not g.trailing or g.values.dtype != np.float64:
+        return None
+    c = coords.lower()
+    nz, ny, nx = g.core_shape
+    ydef = np.asarray(g.coord(1), dtype=np.float64)
+    if c == 'lat-lon':
+        lats = np.deg2rad(ydef)
+        cosG = np.cos(lats)
+        f = 2. * mp['Omega'] * np.sin(lats)
+        rows = np.stack([f ** 2 * cosG, np.cos((lats + _shift1(lats)) / 2.), cosG, cosG])
+    elif c == 'cartesian':
+        f = mp['f0'] + mp['beta'] * ydef
+        rows = np.stack([f ** 2., np.ones(ny), np.ones(ny), np.ones(ny)])
+    else:
+        return None                              # let the host path raise the reference's exception
+    N2 = mp['N2']
+    if hasattr(N2, 'dims'):
+        nd = list(N2.dims)
+        nv = np.ascontiguousarray(np.asarray(N2.values, dtype=np.float64))
+        core_strides = {g.dims[0]: ny * nx, g.dims[1]: nx, g.dims[2]: 1}
+        if nd == g.all_dims and len(g.all_dims) > 3:
+            strides = (nz * ny * nx, ny * nx, nx, 1)
+        elif nd == g.dims:
+            strides = (0, ny * nx, nx, 1)
+        elif len(nd) == 1 and nd[0] in g.dims:
+            k = g.dims.index(nd[0])
+            strides = tuple([0] + [1 if m == k else 0 for m in range(3)])
+        else:
+            return None
+        del core_strides
+    else:
+        nv, strides = np.array([float(N2)]), (0, 0, 0, 0)
+    ps = _cal_params3D(g, coords, mp['Rearth'])
+    ip = _update(ps, ip)
+    if ip['debug']:
+        _print_params(ip)
+    try:
+        S, flags, _ = _device_solvers.solve_standard_3D_rows(
+            g.values, rows, nv, strides, ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1], ip['BCs'][2], ip['del1Sqr'],
+            ip['ratio2Sqr'], ip['ratio1Sqr'], ip['optArg'], _undeftmp, ip['flags'], ip['mxLoop'], ip['tolerance'],
+            ctx=ip.get('ctx'))
     except XinvError as e:
         if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
             return None

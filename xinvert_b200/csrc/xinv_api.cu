@@ -318,6 +318,9 @@ struct BeginArgs {
     // xinv_gen2d_rows: coef[0] = rows [5][ny], coef[6] = user forcing
     int g_mode = 0;
     double g_p1 = 1.0, g_p2 = 1.0;
+    // xinv_std3d_rows: coef[0] = rows [4][ny], coef[1] = N2 (n2_count elements, strides n2_strides), coef[3] = user forcing
+    i64 n2_strides[4] = {0, 0, 0, 0};
+    i64 n2_count = 0;
 };
 
 static int problem_begin(xinv_ctx *c, const BeginArgs &a)
@@ -389,21 +392,50 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     const size_t slice_bytes = (size_t)g.N * sizeof(double);
     cudaEvent_t e0 = c->ev0, e1 = c->ev1;
     XmFront front;
+    X3Front front3;
     pb.front = a.front;
     if (a.front) {
         // the front end hands over A rows, C rows, the user's forcing and the row scale; S is output only
         if (o.ordering != XINV_ORDER_COLOUR || o.engine == XINV_ENGINE_COLOUR)
             return set_err(XINV_E_UNSUPPORTED, "xinv_std2d_rows needs the fused engine (colour ordering)");
         std::string why;
-        if (!fused_plan_supported(pb.kind, false, g, why))
-            return set_err(XINV_E_UNSUPPORTED, "xinv_std2d_rows needs the fused engine: %s", why.c_str());
+        if (a.kind == XD_STD3D ? !fused3_plan_supported(g, why) : !fused_plan_supported(pb.kind, false, g, why))
+            return set_err(XINV_E_UNSUPPORTED, "the device front end needs the fused engine: %s", why.c_str());
         front.on = true;
         front.user_undef = a.user_undef;
         front.out_undef = a.out_undef;
         const size_t row_bytes = (size_t)a.ny * sizeof(double);
         const bool gen = (a.kind == XD_GEN2D);
         front.g_mode = a.g_mode; front.g_p1 = a.g_p1; front.g_p2 = a.g_p2;
-        if (gen && pb.mem_space == XINV_MEM_HOST) {
+        if (a.kind == XD_STD3D) {
+            front3.on = true;
+            front3.user_undef = a.user_undef; front3.out_undef = a.out_undef;
+            for (int m = 0; m < 4; ++m) front3.ns[m] = a.n2_strides[m];
+            if (pb.mem_space == XINV_MEM_HOST) {
+                CK(cudaEventRecord(e0, c->stream));
+                int rc = ensure(c->stage[0], slice_bytes * a.batch);            // S (device only until xinv_end)
+                if (rc) return rc;
+                if ((rc = ensure(c->stage[2 + 3], slice_bytes * a.batch))) return rc;       // user forcing
+                if ((rc = ensure(c->stage[2 + 0], 4 * row_bytes))) return rc;               // the four row vectors
+                if ((rc = ensure(c->stage[2 + 1], sizeof(double) * (size_t)a.n2_count))) return rc;   // N2
+                CK(cudaMemcpyAsync(c->stage[5].p, a.coef[3], slice_bytes * a.batch, cudaMemcpyHostToDevice, c->stream));
+                CK(cudaMemcpyAsync(c->stage[2].p, a.coef[0], 4 * row_bytes, cudaMemcpyHostToDevice, c->stream));
+                CK(cudaMemcpyAsync(c->stage[3].p, a.coef[1], sizeof(double) * (size_t)a.n2_count, cudaMemcpyHostToDevice, c->stream));
+                c->stats.h2d_bytes += (i64)(slice_bytes * a.batch + 4 * row_bytes + sizeof(double) * (size_t)a.n2_count);
+                CK(cudaEventRecord(e1, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                c->stats.h2d_ms = ms;
+                pb.dS = (double *)c->stage[0].p;
+                front3.F = (const double *)c->stage[5].p;
+                front3.rows = (const double *)c->stage[2].p;
+                front3.N2 = (const double *)c->stage[3].p;
+            } else {
+                pb.dS = a.S;
+                front3.F = a.coef[3]; front3.rows = a.coef[0]; front3.N2 = a.coef[1];
+            }
+        } else if (gen && pb.mem_space == XINV_MEM_HOST) {
             CK(cudaEventRecord(e0, c->stream));
             int rc = ensure(c->stage[0], slice_bytes * a.batch);            // S (device only until xinv_end)
             if (rc) return rc;
@@ -501,9 +533,10 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
             const char *e3 = getenv("XINV_FUSED3");
             if (e3 && atoi(e3) == 0) why = "disabled by XINV_FUSED3=0";
             else if (fused3_plan_supported(g, why) &&
-                     fused3_plan_build(pb.fused3, c->xm_work, c->sm_count, g, pb.q, pb.batch, pb.dS, c->stream, why) == 0)
+                     fused3_plan_build(pb.fused3, c->xm_work, c->sm_count, g, pb.q, pb.batch, pb.dS, c->stream, why,
+                                       a.front ? &front3 : nullptr) == 0)
                 pb.engine = XINV_ENGINE_FUSED;
-            if (pb.engine != XINV_ENGINE_FUSED && o.engine == XINV_ENGINE_FUSED)
+            if (pb.engine != XINV_ENGINE_FUSED && (o.engine == XINV_ENGINE_FUSED || a.front))
                 return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
         } else if (fused_plan_supported(pb.kind, pb.hasB, g, why)) {
             rc = fused_plan_build(pb.fused, c->xm_work, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, pb.mxLoop, c->stream, why,
@@ -544,7 +577,8 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
         CK(cudaMemcpy(fl, c->xm_work.p[7], sizeof fl, cudaMemcpyDeviceToHost));
         if (fl[1]) {
             fused_plan_release(pb.fused);
-            return set_err(XINV_E_UNSUPPORTED, "xinv_std2d_rows: an unmasked forcing value is not finite (use xinv_std2d)");
+            fused3_plan_release(pb.fused3);
+            return set_err(XINV_E_UNSUPPORTED, "device front end: an unmasked forcing value is not finite (use the full-array entry)");
         }
     }
     pb.h_nactive = (int)a.batch;
@@ -868,6 +902,40 @@ extern "C" int xinv_std3d_begin(xinv_ctx *ctx, double *S, const double *A, const
     a.p[0] = delxSqr; a.p[1] = ratio2Sqr; a.p[2] = ratio1Sqr;
     a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
     return problem_begin(ctx, a);
+}
+
+extern "C" int xinv_std3d_rows(xinv_ctx *ctx, double *S_out, const double *rows, const double *N2,
+                               const int64_t *n2_strides, int64_t n2_count, const double *F_user,
+                               double user_undef, double out_undef,
+                               int64_t batch, int64_t nz, int64_t ny, int64_t nx, int bcz, int bcy, int bcx,
+                               double delxSqr, double ratio2Sqr, double ratio1Sqr,
+                               double optArg, double undef, double *flags,
+                               int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    if (!valid_bc(bcz)) return set_err(XINV_E_ARG, "bad boundary condition code");
+    if (!rows || !N2 || !n2_strides || !F_user) return set_err(XINV_E_ARG, "rows, N2, n2_strides and F_user must not be NULL");
+    if (n2_count < 1) return set_err(XINV_E_ARG, "n2_count < 1");
+    {   // the largest element N2 is read at must lie inside the buffer
+        const int64_t ext[4] = {batch, nz, ny, nx};
+        int64_t last = 0;
+        for (int m = 0; m < 4; ++m) {
+            if (n2_strides[m] < 0) return set_err(XINV_E_ARG, "n2_strides must be >= 0");
+            if (ext[m] > 0) last += n2_strides[m] * (ext[m] - 1);
+        }
+        if (last >= n2_count) return set_err(XINV_E_ARG, "n2_strides reach element %lld of an N2 buffer of %lld", (long long)last, (long long)n2_count);
+    }
+    BeginArgs a{};
+    a.kind = XD_STD3D; a.S = S_out;
+    a.coef[0] = rows; a.coef[1] = N2; a.coef[2] = rows; a.coef[3] = F_user; a.ncoef = 4; a.b_index = -1;
+    a.batch = batch; a.nz = nz; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delxSqr; a.p[1] = ratio2Sqr; a.p[2] = ratio1Sqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    a.front = true; a.user_undef = user_undef; a.out_undef = out_undef;
+    for (int m = 0; m < 4; ++m) a.n2_strides[m] = n2_strides[m];
+    a.n2_count = n2_count;
+    int rc = problem_begin(ctx, a);
+    if (rc) return rc;
+    return run_to_completion(ctx);
 }
 
 extern "C" int xinv_std2d(xinv_ctx *ctx, double *S, const double *A, const double *B,

@@ -559,6 +559,126 @@ __global__ void x3_unpack_kernel(double *__restrict__ dst, const double *__restr
 }
 
 // ----------------------------------------------------------------------------
+// Front end for invert_omega (xinv_std3d_rows): what apps.__mask_FS, __coeffs_omega and the
+// de-masking of __template do on the host (apps.py:2112-2159, :2016-2052, :1386-1392), on the device.
+//   A[k][j][i] = rows[0][j]                       (f^2 cosG | f^2)
+//   B[k][j][i] = N2(b,k,j,i) * rows[1][j]          (n2 * cosH | n2)            one IEEE multiply, as numpy does
+//   C[k][j][i] = N2(b,k,j,i) / rows[2][j]          (n2 / cosG | n2)            one IEEE division
+//   F          = forcing * rows[3][j] on valid cells (cosG | 1), undef on land
+// N2 is read through four element strides (batch, level, row, column; 0 = broadcast), so a scalar, a profile
+// along any core dimension, a volume shared by the batch and a full array are all the same code.
+// ----------------------------------------------------------------------------
+struct X3Front {
+    bool on = false;
+    const double *rows = nullptr;        // [4][ny] (device)
+    const double *N2 = nullptr;          // (device)
+    i64 ns[4] = {0, 0, 0, 0};
+    const double *F = nullptr;           // user forcing [batch][nz][ny][nx] (device)
+    double user_undef = 0.0, out_undef = 0.0;
+};
+
+__device__ __forceinline__ bool x3_land(double f, double user_undef, double undef)
+{
+    // (a raw value equal to the internal marker is land too: maskF != -9.99e8, apps.py:2036, :1389)
+    return ((user_undef != user_undef) ? (f != f) : (f == user_undef)) | (f == undef);
+}
+
+// B and C of the padded layout for nbBC volumes
+__global__ void x3_front_bc_kernel(double *__restrict__ Bp, double *__restrict__ Cp, const double *__restrict__ rows,
+                                   const double *__restrict__ N2, i64 s0, i64 s1, i64 s2, i64 s3, i64 nz, i64 ny, i64 nx,
+                                   i64 pitch, i64 nbBC, int periodic)
+{
+    const i64 pc = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pc >= pitch) return;
+    const i64 i = pc - XM_PADL;
+    const i64 nrows = nz * ny;
+    bool col = (i >= 0) && (i < nx);
+    i64 iw = i;
+    if (periodic && i >= -XM_GHOST && i < nx + XM_GHOST) { col = true; iw = ((i % nx) + nx) % nx; }
+    for (i64 row = blockIdx.y; row < nrows * nbBC; row += gridDim.y) {
+        const i64 b = row / nrows, r = row - b * nrows;
+        const i64 k = r / ny, j = r - k * ny;
+        double vb = 0.0, vc = 0.0;
+        if (col) {
+            const double n2 = N2[b * s0 + k * s1 + j * s2 + iw * s3];
+            vb = n2 * rows[ny + j];
+            vc = n2 / rows[2 * ny + j];
+        }
+        Bp[row * pitch + pc] = vb;
+        Cp[row * pitch + pc] = vc;
+    }
+}
+
+// Fd (every volume) and fac (nbFac volumes) straight from the user's forcing, N2 and the row vectors.
+// flag[1] |= 1 if a valid forcing value is not finite (the caller then falls back to the host path).
+__global__ void x3_front_derived_kernel(double *__restrict__ Fd, double *__restrict__ fac, const double *__restrict__ rows,
+                                        const double *__restrict__ N2, i64 s0, i64 s1, i64 s2, i64 s3,
+                                        const double *__restrict__ F, i64 nz, i64 ny, i64 nx, i64 pitch, i64 nb, i64 nbFac,
+                                        int periodic, double user_undef, double undef, double delxSqr, double ratio2Sqr,
+                                        double ratio1Sqr, double optArg, int *flag)
+{
+    const i64 pc = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pc >= pitch) return;
+    const i64 i = pc - XM_PADL;
+    const i64 nrows = nz * ny;
+    bool col = true;
+    i64 iw = i, ie = i + 1;
+    if (periodic) {
+        col = (i >= -XM_GHOST) && (i < nx + XM_GHOST);
+        iw = ((i % nx) + nx) % nx;
+        ie = (iw + 1 == nx) ? 0 : iw + 1;
+    } else {
+        col = (i >= 1) && (i <= nx - 2);
+    }
+    for (i64 row = blockIdx.y; row < nrows * nb; row += gridDim.y) {
+        const i64 b = row / nrows, r = row - b * nrows;
+        const i64 k = r / ny, j = r - k * ny;
+        const bool cell = col && (k >= 1) && (k <= nz - 2) && (j >= 1) && (j <= ny - 2);
+        double vF = __hiloint2double(XM_SKIP_HI, 0), vf = 0.0;
+        if (cell) {
+            const double *n2 = N2 + b * s0 + k * s1;
+            const double Au = rows[j], Ac = rows[j];
+            const double Bn = n2[(j + 1) * s2 + iw * s3] * rows[ny + j + 1], Bc = n2[j * s2 + iw * s3] * rows[ny + j];
+            const double Ce = n2[j * s2 + ie * s3] / rows[2 * ny + j], Cc = n2[j * s2 + iw * s3] / rows[2 * ny + j];
+            const double f = F[row * nx + iw];
+            if (!x3_land(f, user_undef, undef)) {
+                if (!isfinite(f)) flag[1] = 1;
+                const double fm = f * rows[3 * ny + j];
+                if ((fm != undef) & (Au != undef) & (Bn != undef) & (Bc != undef) & (Ce != undef) & (Cc != undef))
+                    vF = fm * delxSqr;
+            }
+            vf = optArg / ((Au + Ac) * ratio2Sqr + (Bn + Bc) * ratio1Sqr + (Ce + Cc));
+        }
+        Fd[row * pitch + pc] = vF;
+        if (b < nbFac) fac[row * pitch + pc] = vf;
+    }
+}
+
+// A as row values: vals[v][j] = rows[0][j] for every level v
+__global__ void x3_front_rowvals_kernel(double *__restrict__ vals, const double *__restrict__ rows, i64 nv, i64 ny, i64 rpitch)
+{
+    const i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rpitch) return;
+    for (i64 v = blockIdx.y; v < nv; v += gridDim.y) vals[v * rpitch + j] = (j < ny) ? rows[j] : 0.0;
+}
+
+// ... and the way back: dense S := omega where the forcing was valid, out_undef on land
+__global__ void x3_unpack_front_kernel(double *__restrict__ dst, const double *__restrict__ buf0,
+                                       const double *__restrict__ buf1, const double *__restrict__ F, i64 rows, i64 nx,
+                                       i64 pitch, i64 nb, double user_undef, double out_undef, double undef,
+                                       const XdSliceState *__restrict__ st)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nx) return;
+    for (i64 row = blockIdx.y; row < rows * nb; row += gridDim.y) {
+        const i64 b = row / rows;
+        const double *src = st[b].cur ? buf1 : buf0;
+        const double f = F[row * nx + i];
+        dst[row * nx + i] = x3_land(f, user_undef, undef) ? out_undef : src[row * pitch + XM_PADL + i];
+    }
+}
+
+// ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
 // kernel variants: tile height TJ (TJ - 4 owned rows, TJ warps), ring depth K, CTAs per SM the register
@@ -583,6 +703,7 @@ static const X3Variant X3_VARIANTS[] = {
 
 struct Fused3Plan {
     bool built = false;
+    X3Front front;
     int variant = 0;
     bool arow = false;             // A constant along x: AROW kernels
     bool coop = false;
@@ -679,15 +800,18 @@ static void x3_choose(i64 nz, i64 ny, i64 nx, i64 batch, int sm_count, int *vari
 }
 
 static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, const XdGeom &g, const XdCoef &q, i64 batch,
-                                    double *dS, cudaStream_t stream, std::string &why)
+                                    double *dS, cudaStream_t stream, std::string &why, const X3Front *front = nullptr)
 {
     fused3_plan_release(p);
+    if (front) p.front = *front;
+    const bool fe = p.front.on;                  // front end: row vectors + N2 + user forcing, zero initial guess
     const i64 nz = g.nz, ny = g.ny, nx = g.nx;
     const i64 pitch = ((XM_PADL + nx + XM_GHOST) + 3) / 4 * 4;
     const int periodic = (g.bcx == XD_BC_PERIODIC);
     const i64 rows = nz * ny;
     const size_t vol_bytes = (size_t)rows * pitch * sizeof(double);
-    const int cb[4] = {q.cs[0] != 0, q.cs[1] != 0, q.cs[2] != 0, q.cs[3] != 0};
+    const int feb = fe && p.front.ns[0] != 0;    // front end: N2 (hence B, C and the factor) has a batch axis
+    const int cb[4] = {fe ? 0 : q.cs[0] != 0, fe ? feb : q.cs[1] != 0, fe ? feb : q.cs[2] != 0, fe ? 1 : q.cs[3] != 0};
     const int cbFac = cb[0] | cb[1] | cb[2];
     const int cbFd = cbFac | cb[3];
     if ((i64)nz * batch > 0x7ffffff0) { why = "too many levels x slices for one tensor map"; return -1; }
@@ -712,8 +836,10 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
     // ---- is A constant along x?  (one pass over it, one 4-byte read-back) ----
     {
         const char *ea = getenv("XINV_FUSED3_AROW");
-        p.arow = !(ea && atoi(ea) == 0);
-        if (p.arow) {
+        p.arow = fe || !(ea && atoi(ea) == 0);
+        if (fe) {
+            cudaMemsetAsync(flag, 0, 8, stream);
+        } else if (p.arow) {
             const i64 nrA = rows * (cb[0] ? batch : 1);
             cudaMemsetAsync(flag, 0, 4, stream);
             x3_rowconst_kernel<<<gridfor(nx, nrA), blk, 0, stream>>>(q.c[0], nrA, nx, (int *)flag);
@@ -748,14 +874,27 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
     auto pack = [&](void *dst, const double *src, i64 bstride, i64 nb) {
         x3_pack_kernel<<<gridfor(pitch, rows * nb), blk, 0, stream>>>((double *)dst, src, rows, nx, pitch, bstride, nb, periodic);
     };
-    pack(p.bufS[0], dS, g.N, batch);
-    pack(p.bufS[1], dS, g.N, batch);       // levels 0 / nz-1 and all pad columns of both buffers start identical
-    if (p.arow) x3_pack_rowvals_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, q.c[0], nvA, ny, nx, rpitch);
-    else        pack(p.bufA, q.c[0], q.cs[0], cb[0] ? batch : 1);
-    pack(p.bufB, q.c[1], q.cs[1], cb[1] ? batch : 1);
-    pack(p.bufC, q.c[2], q.cs[2], cb[2] ? batch : 1);
-    x3_pack_derived_kernel<<<gridfor(pitch, rows * (cbFd ? batch : 1)), blk, 0, stream>>>(
-        (double *)p.bufFd, (double *)p.bufFac, q, nz, ny, nx, pitch, cbFd ? batch : 1, cbFac ? batch : 1, periodic);
+    if (fe) {
+        const X3Front &f = p.front;
+        cudaMemsetAsync(p.bufS[0], 0, vol_bytes * batch, stream);      // zero initial guess (apps.py:2145), ghosts included
+        cudaMemsetAsync(p.bufS[1], 0, vol_bytes * batch, stream);
+        x3_front_rowvals_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, f.rows, nvA, ny, rpitch);
+        x3_front_bc_kernel<<<gridfor(pitch, rows * (feb ? batch : 1)), blk, 0, stream>>>(
+            (double *)p.bufB, (double *)p.bufC, f.rows, f.N2, f.ns[0], f.ns[1], f.ns[2], f.ns[3], nz, ny, nx, pitch,
+            feb ? batch : 1, periodic);
+        x3_front_derived_kernel<<<gridfor(pitch, rows * batch), blk, 0, stream>>>(
+            (double *)p.bufFd, (double *)p.bufFac, f.rows, f.N2, f.ns[0], f.ns[1], f.ns[2], f.ns[3], f.F, nz, ny, nx, pitch,
+            batch, feb ? batch : 1, periodic, f.user_undef, q.undef, q.p[0], q.p[1], q.p[2], q.optArg, (int *)flag);
+    } else {
+        pack(p.bufS[0], dS, g.N, batch);
+        pack(p.bufS[1], dS, g.N, batch);   // levels 0 / nz-1 and all pad columns of both buffers start identical
+        if (p.arow) x3_pack_rowvals_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, q.c[0], nvA, ny, nx, rpitch);
+        else        pack(p.bufA, q.c[0], q.cs[0], cb[0] ? batch : 1);
+        pack(p.bufB, q.c[1], q.cs[1], cb[1] ? batch : 1);
+        pack(p.bufC, q.c[2], q.cs[2], cb[2] ? batch : 1);
+        x3_pack_derived_kernel<<<gridfor(pitch, rows * (cbFd ? batch : 1)), blk, 0, stream>>>(
+            (double *)p.bufFd, (double *)p.bufFac, q, nz, ny, nx, pitch, cbFd ? batch : 1, cbFac ? batch : 1, periodic);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) {
         why = std::string("pack kernels: ") + cudaGetErrorString(e);
         fused3_plan_release(p);
@@ -865,6 +1004,10 @@ static inline int fused3_unpack(Fused3Plan &p, double *dS, const XdSliceState *s
     i64 gy = rows * p.batch;
     if (gy > 32768) gy = 32768;
     dim3 grid((unsigned)((a.nx + 127) / 128), (unsigned)gy, 1);
-    x3_unpack_kernel<<<grid, 128, 0, stream>>>(dS, a.Sbuf[0], a.Sbuf[1], rows, a.nx, a.pitch, p.batch, st);
+    if (p.front.on)
+        x3_unpack_front_kernel<<<grid, 128, 0, stream>>>(dS, a.Sbuf[0], a.Sbuf[1], p.front.F, rows, a.nx, a.pitch, p.batch,
+                                                         p.front.user_undef, p.front.out_undef, a.undef, st);
+    else
+        x3_unpack_kernel<<<grid, 128, 0, stream>>>(dS, a.Sbuf[0], a.Sbuf[1], rows, a.nx, a.pitch, p.batch, st);
     return 0;
 }

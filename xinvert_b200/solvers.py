@@ -285,6 +285,47 @@ def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_unde
     return S, fl, stats
 
 
+def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, BCz, BCy, BCx, delxSqr, ratio2Sqr,
+                           ratio1Sqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
+                           check_every=0, ctx=None):
+    """invert_omega front end (``xinv_std3d_rows``): the user's forcing ``F_user[..., nz, ny, nx]`` (host numpy
+    array), ``rows[4, ny]`` (A; the factor of B = N2 * rows[1]; the divisor of C = N2 / rows[2]; the forcing
+    scale) and ``N2`` (a float64 buffer read through four element strides: batch, level, row, column; 0 =
+    broadcast).  Returns ``(S, flags[batch, 3], stats)``: solved from a zero initial guess, land = ``out_undef``
+    (what apps.__mask_FS / __coeffs_omega / __template do on the host, on the device)."""
+    L = _lib.load()
+    ctx = ctx or _lib.default_context()
+    Fh = _host_f64(F_user, "F")
+    shape = Fh.shape
+    if len(shape) < 3:
+        raise ValueError("forcing needs at least 3 dimensions")
+    nz, ny, nx = (int(n) for n in shape[-3:])
+    batch = int(np.prod(shape[:-3], dtype=np.int64)) if len(shape) > 3 else 1
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    if rows.shape != (4, ny):
+        raise ValueError(f"rows must have shape (4, {ny})")
+    n2 = np.ascontiguousarray(N2, dtype=np.float64).reshape(-1)
+    st4 = (C.c_int64 * 4)(*[int(v) for v in n2_strides])
+    S = _lib.pinned_empty(shape)
+    opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
+    fl = _flags_array(flags, batch)
+    stats = None
+    N = nz * ny * nx
+    with ctx.lock:
+        for lo, hi in _batch_chunks(batch):
+            o = 8 * lo * N
+            n2_off = 8 * lo * int(n2_strides[0])
+            rc = L.xinv_std3d_rows(ctx.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
+                                   C.c_void_p(n2.ctypes.data + n2_off), st4, int(n2.size - lo * int(n2_strides[0])),
+                                   C.c_void_p(Fh.ctypes.data + o), float(user_undef), float(out_undef), hi - lo, nz, ny, nx,
+                                   _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delxSqr),
+                                   float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
+                                   C.c_void_p(fl[lo:hi].ctypes.data), int(mxLoop), float(tolerance), C.byref(opts))
+            _lib.check(rc)
+            stats = _merge_stats(stats, ctx.stats())
+    return S, fl, stats
+
+
 def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ratioQtr,
                      ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
                      tolerance=1e-8, ordering="colour", engine="auto", check_every=0, ctx=None, profile=False):
