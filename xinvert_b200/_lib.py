@@ -200,6 +200,23 @@ def default_context(device=0):
     return ctx
 
 
+_pipe_ctx = {}
+
+
+def pipeline_contexts(device, n):
+    """``n`` contexts on ``device`` (the first is the default context): every context has its own stream and
+    staging buffers, so calls on different contexts overlap on the device -- one context's host<->device copies
+    run while another's kernels do (solvers._execute pipelines the chunks of a batch this way)."""
+    out = [default_context(device)]
+    with _default_ctx_lock:
+        extra = _pipe_ctx.setdefault(device, [])
+        extra[:] = [c for c in extra if c._h]
+        while len(extra) < n - 1:
+            extra.append(Context(device))
+        out += extra[:n - 1]
+    return out
+
+
 def make_opts(ordering="colour", mem_space=MEM_HOST, engine="auto", check_every=0,
               coef_strides=None, profile=False):
     o = XinvOpts()

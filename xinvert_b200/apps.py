@@ -408,17 +408,17 @@ def _poisson_device_front(F, dims, coords, icbc, mParams, iParams):
     if ip['debug']:
         _print_params(ip)
     try:
-        S, flags, _ = _device_solvers.solve_standard_2D_rows(
+        S, flags, stats = _device_solvers.solve_standard_2D_rows(
             g.values, A_rows, C_rows, scale, ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1], ip['del1Sqr'],
             ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp, ip['flags'], ip['mxLoop'], ip['tolerance'],
-            ctx=ip.get('ctx'))
+            ctx=ip.get('ctx'), devices=ip.get('devices'))
     except XinvError as e:
         if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
             return None
         raise
     _, noncore, _ = core._layout(F, dims)
     core._report(ip, core._slice_labels(F, noncore), flags)
-    _report_flags(iParams, flags)
+    _report_flags(iParams, flags, stats)
     return wrap_like(F, S, name='inverted')
 
 
@@ -550,17 +550,17 @@ def _general_device_front(rows_func, valid, F, dims, coords, icbc, mParams, iPar
     if ip['debug']:
         _print_params(ip)
     try:
-        S, flags, _ = _device_solvers.solve_general_2D_rows(
+        S, flags, stats = _device_solvers.solve_general_2D_rows(
             g.values, rows, r['g_mode'], r['g_p1'], r['g_p2'], ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1],
             ip['del1'], ip['del1Sqr'], ip['ratio'], ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp,
-            ip['flags'], ip['mxLoop'], ip['tolerance'], ctx=ip.get('ctx'))
+            ip['flags'], ip['mxLoop'], ip['tolerance'], ctx=ip.get('ctx'), devices=ip.get('devices'))
     except XinvError as e:
         if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
             return None
         raise
     _, noncore, _ = core._layout(F, dims)
     core._report(ip, core._slice_labels(F, noncore), flags)
-    _report_flags(iParams, flags)
+    _report_flags(iParams, flags, stats)
     return wrap_like(F, S, name='inverted')
 
 
@@ -614,17 +614,17 @@ def _omega_device_front(F, dims, coords, icbc, mParams, iParams):
     if ip['debug']:
         _print_params(ip)
     try:
-        S, flags, _ = _device_solvers.solve_standard_3D_rows(
+        S, flags, stats = _device_solvers.solve_standard_3D_rows(
             g.values, rows, nv, strides, ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1], ip['BCs'][2], ip['del1Sqr'],
             ip['ratio2Sqr'], ip['ratio1Sqr'], ip['optArg'], _undeftmp, ip['flags'], ip['mxLoop'], ip['tolerance'],
-            ctx=ip.get('ctx'))
+            ctx=ip.get('ctx'), devices=ip.get('devices'))
     except XinvError as e:
         if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
             return None
         raise
     _, noncore, _ = core._layout(F, dims)
     core._report(ip, core._slice_labels(F, noncore), flags)
-    _report_flags(iParams, flags)
+    _report_flags(iParams, flags, stats)
     return wrap_like(F, S, name='inverted')
 
 
@@ -679,11 +679,14 @@ def _coeffs_omega(g, coords, mParams, iParams, icbc):
     return maskF, Fm, initS, (A, B, C)
 
 
-def _report_flags(user_iParams, flags):
-    """Per-slice flags [batch, 3] go back to the caller's own iParams dict (an addition to the
-    reference's interface, the same on every path) -- never into the module-level defaults."""
+def _report_flags(user_iParams, flags, stats=None):
+    """Per-slice flags [batch, 3] (and the library's statistics of the call) go back to the caller's own
+    iParams dict (an addition to the reference's interface, the same on every path) -- never into the
+    module-level defaults."""
     if isinstance(user_iParams, dict) and user_iParams is not default_iParams:
         user_iParams['flags_all'] = flags
+        if stats is not None:
+            user_iParams['stats'] = stats
 
 
 def _print_params(iParams):
@@ -722,7 +725,7 @@ def _template(coef_func, inv_func, dimLen, F, dims, coords='lat-lon', icbc=None,
     Ff = wrap_like(F, forcing)
     inv_func(*coeffs, Ff, S, dims, iParams)
     if 'flags_all' in iParams:
-        _report_flags(user_iParams, iParams['flags_all'])
+        _report_flags(user_iParams, iParams['flags_all'], iParams.get('stats'))
 
     ######  4. properly de-masking  ######
     out = np.asarray(S.values)                   # our own array (built from initS), free to modify

@@ -17,6 +17,9 @@ semantics up to the documented ordering difference):
                 trajectory, much slower on a GPU)
   ``engine``    'auto' | 'colour' | 'fused'
   ``ctx``       an ``xinvert_b200.Context`` (device / stream); default: device 0
+  ``devices``   list of GPU indices: the flattened batch is cut into contiguous blocks
+                (distributed.shard_bounds), one context and one thread per GPU from this process;
+                per-slice results are those of a single GPU (slices are independent solves)
 After the call ``iParams['flags']`` holds the flags of the LAST slice (what the
 reference's shared flags array ends up with) and ``iParams['flags_all']`` the
 ``[batch, 3]`` array of every slice.
@@ -79,7 +82,7 @@ def _report(iParams, labels, flags):
         print(info + " loops {0:4.0f} and tolerance is {1:e}".format(fl[2], fl[1]) + tail)
 
 
-def _finish(S, result, order, iParams, labels, flags):
+def _finish(S, result, order, iParams, labels, flags, stats=None):
     inv = np.argsort(order)
     out = np.transpose(result, inv)
     sv = S.values
@@ -88,6 +91,8 @@ def _finish(S, result, order, iParams, labels, flags):
     if not same:                                # (the solve ran in place on S.values when no re-layout was needed)
         sv[...] = out.astype(sv.dtype, copy=False)
     iParams["flags_all"] = flags
+    if stats is not None:
+        iParams["stats"] = stats
     fl = iParams.get("flags")
     if isinstance(fl, np.ndarray) and fl.shape == (3,):
         fl[:] = flags[-1]
@@ -99,7 +104,7 @@ def _finish(S, result, order, iParams, labels, flags):
 
 def _engine_kw(iParams):
     return dict(ordering=iParams.get("ordering", "colour"), engine=iParams.get("engine", "auto"),
-                ctx=iParams.get("ctx"))
+                ctx=iParams.get("ctx"), devices=iParams.get("devices"))
 
 
 def _flags_in(iParams):
@@ -115,11 +120,11 @@ def inv_standard2D(A, B, C, F, S, dims, iParams):
     all_dims, noncore, order = _layout(F, dims)
     arrs = [_as_batched(X, all_dims, order, dims, n) for X, n in ((S, "S"), (A, "A"), (B, "B"), (C, "C"), (F, "F"))]
     Sv, Av, Bv, Cv, Fv = arrs
-    flags, _ = solvers.solve_standard_2D(
+    flags, stats = solvers.solve_standard_2D(
         Sv, Av, Bv, Cv, Fv, iParams["BCs"][0], iParams["BCs"][1], iParams["del1Sqr"], iParams["ratioQtr"],
         iParams["ratioSqr"], iParams["optArg"], _undeftmp, _flags_in(iParams), iParams["mxLoop"],
         iParams["tolerance"], **_engine_kw(iParams))
-    return _finish(S, Sv, order, iParams, _slice_labels(F, noncore), flags)
+    return _finish(S, Sv, order, iParams, _slice_labels(F, noncore), flags, stats)
 
 
 def inv_general2D(A, B, C, D, E, F, G, S, dims, iParams):
@@ -131,11 +136,11 @@ def inv_general2D(A, B, C, D, E, F, G, S, dims, iParams):
     names = ("S", "A", "B", "C", "D", "E", "F", "G")
     Sv, Av, Bv, Cv, Dv, Ev, Fv, Gv = [_as_batched(X, all_dims, order, dims, n)
                                       for X, n in zip((S, A, B, C, D, E, F, G), names)]
-    flags, _ = solvers.solve_general_2D(
+    flags, stats = solvers.solve_general_2D(
         Sv, Av, Bv, Cv, Dv, Ev, Fv, Gv, iParams["BCs"][0], iParams["BCs"][1], iParams["del1"], iParams["del1Sqr"],
         iParams["ratio"], iParams["ratioQtr"], iParams["ratioSqr"], iParams["optArg"], _undeftmp,
         _flags_in(iParams), iParams["mxLoop"], iParams["tolerance"], **_engine_kw(iParams))
-    return _finish(S, Sv, order, iParams, _slice_labels(G, noncore), flags)
+    return _finish(S, Sv, order, iParams, _slice_labels(G, noncore), flags, stats)
 
 
 def inv_standard3D(A, B, C, F, S, dims, iParams):
@@ -146,8 +151,8 @@ def inv_standard3D(A, B, C, F, S, dims, iParams):
     all_dims, noncore, order = _layout(F, dims)
     Sv, Av, Bv, Cv, Fv = [_as_batched(X, all_dims, order, dims, n)
                           for X, n in ((S, "S"), (A, "A"), (B, "B"), (C, "C"), (F, "F"))]
-    flags, _ = solvers.solve_standard_3D(
+    flags, stats = solvers.solve_standard_3D(
         Sv, Av, Bv, Cv, Fv, iParams["BCs"][0], iParams["BCs"][1], iParams["BCs"][2], iParams["del1Sqr"],
         iParams["ratio2Sqr"], iParams["ratio1Sqr"], iParams["optArg"], _undeftmp, _flags_in(iParams),
         iParams["mxLoop"], iParams["tolerance"], **_engine_kw(iParams))
-    return _finish(S, Sv, order, iParams, _slice_labels(F, noncore), flags)
+    return _finish(S, Sv, order, iParams, _slice_labels(F, noncore), flags, stats)

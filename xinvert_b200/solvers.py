@@ -149,34 +149,123 @@ def _sync_torch_stream(device_array):
     torch.cuda.current_stream(device_array.device).synchronize()
 
 
-def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, profile=False, S_dev=None):
+# ---------------------------------------------------------------------------
+# Execution plan of one batched call: slices are independent solves (core.py:129-139), so the flattened batch
+# may be cut anywhere.  It is cut (a) over the devices named in ``devices`` (contiguous blocks,
+# distributed.shard_bounds -- what a multi-process launch does rank by rank, from one process: one context and
+# one thread per GPU), and (b) on each device into chunks that are pipelined through two contexts (two streams,
+# two sets of staging buffers): while one chunk is being solved the next one is copied to the device and the
+# previous result is copied back.  Every slice still stops on its own test; results do not depend on the cut.
+# ---------------------------------------------------------------------------
+PIPE_MIN_CELLS = 4 << 20          # a chunk keeps at least this many cells (enough work to fill the GPU)
+PIPE_STREAMS = 2
+
+
+def _plan(batch, cells_per_slice, devices, pipelined):
+    """[(device, worker, lo, hi), ...]: the blocks of slices and who runs them."""
+    from .distributed import shard_bounds
+    devices = list(devices) if devices else [0]
+    items = []
+    for r, dev in enumerate(devices):
+        lo, hi = shard_bounds(batch, len(devices), r)
+        n = hi - lo
+        if n <= 0:
+            continue
+        nchunk = 1
+        if pipelined:
+            nchunk = max(1, min(n, (n * cells_per_slice) // PIPE_MIN_CELLS))
+            if nchunk > 1:
+                nchunk = max(nchunk, PIPE_STREAMS)
+            nchunk = min(nchunk, 4 * PIPE_STREAMS)          # a few chunks are enough to hide the copies
+        nchunk = max(nchunk, -(-n // MAX_BATCH))
+        for k in range(nchunk):
+            clo, chi = shard_bounds(n, nchunk, k)
+            if chi > clo:
+                items.append((dev, k % PIPE_STREAMS if nchunk > 1 else 0, lo + clo, lo + chi))
+    return items
+
+
+def _execute(call, batch, cells_per_slice, ctx, devices, host, _contexts=None):
+    """Run ``call(ctx, lo, hi)`` (one C-ABI call on slices [lo, hi), returns that call's stats) over the whole batch.
+    An explicit ``ctx`` (and no ``devices``) pins everything to that context; otherwise the plan above is used."""
+    if batch <= 0:
+        c = ctx or (_contexts or _lib.pipeline_contexts)((list(devices) if devices else [0])[0], 1)[0]
+        with c.lock:
+            return call(c, 0, 0)
+    if ctx is not None and not devices:
+        stats = None
+        with ctx.lock:
+            for lo, hi in _batch_chunks(batch):
+                stats = _merge_stats(stats, call(ctx, lo, hi))
+        return stats
+    if ctx is not None and devices and list(devices) == [ctx.device]:
+        first = {ctx.device: ctx}
+    else:
+        first = {}
+    items = _plan(batch, cells_per_slice, devices, pipelined=host)
+    workers = {}
+    for dev, w, lo, hi in items:
+        workers.setdefault((dev, w), []).append((lo, hi))
+    ctxs = {}
+    for dev in sorted({d for d, _ in workers}):
+        n = 1 + max(w for d, w in workers if d == dev)
+        cs = (_contexts or _lib.pipeline_contexts)(dev, n)
+        if dev in first:
+            cs = [first[dev]] + [c for c in cs if c is not first[dev]][:n - 1]
+        for w in range(n):
+            ctxs[(dev, w)] = cs[w]
+
+    def work(key):
+        c, st = ctxs[key], None
+        for lo, hi in workers[key]:
+            with c.lock:
+                st = _merge_stats(st, call(c, lo, hi))
+        return st
+
+    keys = sorted(workers)
+    if len(keys) == 1:
+        return work(keys[0])
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(keys)) as ex:       # ctypes releases the GIL for the whole C call
+        results = list(ex.map(work, keys))
+    stats = None
+    for st in results:
+        stats = _merge_stats(stats, st)
+    stats["pipeline"] = {"devices": sorted({d for d, _ in keys}), "workers": len(keys), "chunks": len(items)}
+    return stats
+
+
+def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, profile=False, S_dev=None, devices=None):
     L = _lib.load()
-    ctx = ctx or _lib.default_context()
-    opts = _lib.make_opts(ordering=ordering, mem_space=_lib.MEM_DEVICE if ops.device else _lib.MEM_HOST,
-                          engine=engine, check_every=check_every, coef_strides=ops.strides,
-                          profile=profile)
     fl = _flags_array(flags, ops.batch)
     fn = {"std2d": L.xinv_std2d, "gen2d": L.xinv_gen2d, "std3d": L.xinv_std3d}[kind]
-    if ops.device and S_dev is not None:
-        _sync_torch_stream(S_dev)
-    stats = None
-    with ctx.lock:
-        for lo, hi in _batch_chunks(ops.batch):
-            off = lambda p, stride: C.c_void_p(p + 8 * lo * stride) if p is not None else None
-            ptr_args = [off(ops.S_ptr, ops.N)] + [off(p, st) for p, st in zip(ops.ptrs, ops.strides)]
-            flc = fl[lo:hi]                          # contiguous rows of the flags array
-            rc = fn(ctx.handle, *ptr_args, *fn_args_tail(flc, hi - lo), C.byref(opts))
-            _lib.check(rc)
-            stats = _merge_stats(stats, ctx.stats())
+    if ops.device:
+        if S_dev is not None:
+            _sync_torch_stream(S_dev)
+        if ctx is None:
+            ctx = _lib.default_context(getattr(getattr(S_dev, "device", None), "index", None) or 0)
+        devices = None                           # the tensors live on one device
+
+    def call(c, lo, hi):
+        opts = _lib.make_opts(ordering=ordering, mem_space=_lib.MEM_DEVICE if ops.device else _lib.MEM_HOST,
+                              engine=engine, check_every=check_every, coef_strides=ops.strides, profile=profile)
+        off = lambda p, stride: C.c_void_p(p + 8 * lo * stride) if p is not None else None
+        ptr_args = [off(ops.S_ptr, ops.N)] + [off(p, st) for p, st in zip(ops.ptrs, ops.strides)]
+        rc = fn(c.handle, *ptr_args, *fn_args_tail(fl[lo:hi], hi - lo), C.byref(opts))
+        _lib.check(rc)
+        return c.stats()
+
+    stats = _execute(call, ops.batch, ops.N, ctx, devices, host=not ops.device)
     ops.finish()
     return fl, stats
 
 
 def solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg,
                       undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
-                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False):
+                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False, devices=None):
     """Batched ``invert_standard_2D`` (numbas.py:215-416) over S[..., ny, nx], in place.
 
+    ``devices``: GPUs to cut the batch over (one context and one thread per GPU, from this process).
     Returns ``(flags[batch, 3], stats)``."""
     B = _zero_to_none(B)
     ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("F", F)], 2)
@@ -184,12 +273,12 @@ def solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, opt
     tail = lambda fl, nb: (nb, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
                            float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
                            C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
-    return _run("std2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S)
+    return _run("std2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices)
 
 
 def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_undef, BCy, BCx,
                            delxSqr, ratioQtr, ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0),
-                           mxLoop=5000, tolerance=1e-8, check_every=0, ctx=None, out=None):
+                           mxLoop=5000, tolerance=1e-8, check_every=0, ctx=None, out=None, devices=None):
     """Poisson-type front end (``xinv_std2d_rows``): the user's forcing ``F_user[..., ny, nx]`` (host
     numpy array or CUDA tensor; cells equal to ``user_undef`` -- any NaN when that is NaN -- are
     land), per-row coefficients ``A_rows[ny]``, ``C_rows[ny]`` and an optional per-row forcing scale;
@@ -198,9 +287,10 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
     host (apps.py:2112-2159, :1397-1437, :1386-1392) happens on the device; results are identical.
     Raises ``XinvError`` (code -5) when the fused engine cannot take the problem."""
     L = _lib.load()
-    ctx = ctx or _lib.default_context()
     device = _is_device_array(F_user)
     if device:
+        ctx = ctx or _lib.default_context(F_user.device.index or 0)
+        devices = None
         import torch
         if F_user.dtype != torch.float64 or not F_user.is_contiguous():
             raise ValueError("device forcing must be a contiguous float64 tensor")
@@ -231,33 +321,33 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
     for v, name in ((rows[0], "A_rows"), (rows[1], "C_rows"), (rows[2], "F_row_scale")):
         if v is not None and tuple(v.shape) != (ny,):
             raise ValueError(f"{name} must have shape ({ny},)")
-    opts = _lib.make_opts(mem_space=_lib.MEM_DEVICE if device else _lib.MEM_HOST, check_every=check_every)
     fl = _flags_array(flags, batch)
-    stats = None
-    with ctx.lock:
-        for lo, hi in _batch_chunks(batch):
-            off = lambda p: C.c_void_p(p.value + 8 * lo * ny * nx)
-            rc = L.xinv_std2d_rows(ctx.handle, off(S_ptr), ptr(rows[0]), ptr(rows[1]), off(F_ptr), ptr(rows[2]),
-                                   float(user_undef), float(out_undef), hi - lo, ny, nx, _lib.BC_CODES[BCy],
-                                   _lib.BC_CODES[BCx], float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg),
-                                   float(undef), C.c_void_p(fl[lo:hi].ctypes.data), int(mxLoop), float(tolerance),
-                                   C.byref(opts))
-            _lib.check(rc)
-            stats = _merge_stats(stats, ctx.stats())
+
+    def call(c, lo, hi):
+        opts = _lib.make_opts(mem_space=_lib.MEM_DEVICE if device else _lib.MEM_HOST, check_every=check_every)
+        off = lambda p: C.c_void_p(p.value + 8 * lo * ny * nx)
+        rc = L.xinv_std2d_rows(c.handle, off(S_ptr), ptr(rows[0]), ptr(rows[1]), off(F_ptr), ptr(rows[2]),
+                               float(user_undef), float(out_undef), hi - lo, ny, nx, _lib.BC_CODES[BCy],
+                               _lib.BC_CODES[BCx], float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg),
+                               float(undef), C.c_void_p(fl[lo:hi].ctypes.data), int(mxLoop), float(tolerance),
+                               C.byref(opts))
+        _lib.check(rc)
+        return c.stats()
+
+    stats = _execute(call, batch, ny * nx, ctx, devices, host=not device)
     del keep
     return S, fl, stats
 
 
 def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_undef, BCy, BCx, delx, delxSqr, ratio,
                           ratioQtr, ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
-                          tolerance=1e-8, check_every=0, ctx=None):
+                          tolerance=1e-8, check_every=0, ctx=None, devices=None):
     """General-form front end (``xinv_gen2d_rows``): the user's forcing ``G_user[..., ny, nx]`` (host
     numpy array), ``rows[5, ny]`` = A, C, D, E, F of every row, and the forcing transform (``g_mode`` 0:
     G = forcing; 1: G = ((-forcing) / g_p1) / g_p2); returns ``(S, flags[batch, 3], stats)`` with ``S``
     solved from a zero initial guess and land set to ``out_undef`` (what apps.__mask_FS /
     __coeffs_GillMatsuno / __coeffs_Stommel / __template do on the host, on the device)."""
     L = _lib.load()
-    ctx = ctx or _lib.default_context()
     Gh = _host_f64(G_user, "G")
     shape = Gh.shape
     if len(shape) < 2:
@@ -268,33 +358,33 @@ def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_unde
     if rows.shape != (5, ny):
         raise ValueError(f"rows must have shape (5, {ny})")
     S = _lib.pinned_empty(shape)
-    opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
     fl = _flags_array(flags, batch)
-    stats = None
-    with ctx.lock:
-        for lo, hi in _batch_chunks(batch):
-            o = 8 * lo * ny * nx
-            rc = L.xinv_gen2d_rows(ctx.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
-                                   C.c_void_p(Gh.ctypes.data + o), int(g_mode), float(g_p1), float(g_p2),
-                                   float(user_undef), float(out_undef), hi - lo, ny, nx, _lib.BC_CODES[BCy],
-                                   _lib.BC_CODES[BCx], float(delx), float(delxSqr), float(ratio), float(ratioQtr),
-                                   float(ratioSqr), float(optArg), float(undef), C.c_void_p(fl[lo:hi].ctypes.data),
-                                   int(mxLoop), float(tolerance), C.byref(opts))
-            _lib.check(rc)
-            stats = _merge_stats(stats, ctx.stats())
+
+    def call(c, lo, hi):
+        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
+        o = 8 * lo * ny * nx
+        rc = L.xinv_gen2d_rows(c.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
+                               C.c_void_p(Gh.ctypes.data + o), int(g_mode), float(g_p1), float(g_p2),
+                               float(user_undef), float(out_undef), hi - lo, ny, nx, _lib.BC_CODES[BCy],
+                               _lib.BC_CODES[BCx], float(delx), float(delxSqr), float(ratio), float(ratioQtr),
+                               float(ratioSqr), float(optArg), float(undef), C.c_void_p(fl[lo:hi].ctypes.data),
+                               int(mxLoop), float(tolerance), C.byref(opts))
+        _lib.check(rc)
+        return c.stats()
+
+    stats = _execute(call, batch, ny * nx, ctx, devices, host=True)
     return S, fl, stats
 
 
 def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, BCz, BCy, BCx, delxSqr, ratio2Sqr,
                            ratio1Sqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
-                           check_every=0, ctx=None):
+                           check_every=0, ctx=None, devices=None):
     """invert_omega front end (``xinv_std3d_rows``): the user's forcing ``F_user[..., nz, ny, nx]`` (host numpy
     array), ``rows[4, ny]`` (A; the factor of B = N2 * rows[1]; the divisor of C = N2 / rows[2]; the forcing
     scale) and ``N2`` (a float64 buffer read through four element strides: batch, level, row, column; 0 =
     broadcast).  Returns ``(S, flags[batch, 3], stats)``: solved from a zero initial guess, land = ``out_undef``
     (what apps.__mask_FS / __coeffs_omega / __template do on the host, on the device)."""
     L = _lib.load()
-    ctx = ctx or _lib.default_context()
     Fh = _host_f64(F_user, "F")
     shape = Fh.shape
     if len(shape) < 3:
@@ -307,28 +397,29 @@ def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, 
     n2 = np.ascontiguousarray(N2, dtype=np.float64).reshape(-1)
     st4 = (C.c_int64 * 4)(*[int(v) for v in n2_strides])
     S = _lib.pinned_empty(shape)
-    opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
     fl = _flags_array(flags, batch)
-    stats = None
     N = nz * ny * nx
-    with ctx.lock:
-        for lo, hi in _batch_chunks(batch):
-            o = 8 * lo * N
-            n2_off = 8 * lo * int(n2_strides[0])
-            rc = L.xinv_std3d_rows(ctx.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
-                                   C.c_void_p(n2.ctypes.data + n2_off), st4, int(n2.size - lo * int(n2_strides[0])),
-                                   C.c_void_p(Fh.ctypes.data + o), float(user_undef), float(out_undef), hi - lo, nz, ny, nx,
-                                   _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delxSqr),
-                                   float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
-                                   C.c_void_p(fl[lo:hi].ctypes.data), int(mxLoop), float(tolerance), C.byref(opts))
-            _lib.check(rc)
-            stats = _merge_stats(stats, ctx.stats())
+
+    def call(c, lo, hi):
+        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
+        o = 8 * lo * N
+        n2_off = 8 * lo * int(n2_strides[0])
+        rc = L.xinv_std3d_rows(c.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
+                               C.c_void_p(n2.ctypes.data + n2_off), st4, int(n2.size - lo * int(n2_strides[0])),
+                               C.c_void_p(Fh.ctypes.data + o), float(user_undef), float(out_undef), hi - lo, nz, ny, nx,
+                               _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delxSqr),
+                               float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
+                               C.c_void_p(fl[lo:hi].ctypes.data), int(mxLoop), float(tolerance), C.byref(opts))
+        _lib.check(rc)
+        return c.stats()
+
+    stats = _execute(call, batch, N, ctx, devices, host=True)
     return S, fl, stats
 
 
 def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ratioQtr,
                      ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
-                     tolerance=1e-8, ordering="colour", engine="auto", check_every=0, ctx=None, profile=False):
+                     tolerance=1e-8, ordering="colour", engine="auto", check_every=0, ctx=None, profile=False, devices=None):
     """Batched ``invert_general_2D`` (numbas.py:987-1201) over S[..., ny, nx], in place."""
     B = _zero_to_none(B)
     ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("D", D), ("E", E), ("F", F), ("G", G)], 2)
@@ -336,19 +427,19 @@ def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ra
     tail = lambda fl, nb: (nb, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
                            float(delx), float(delxSqr), float(ratio), float(ratioQtr), float(ratioSqr),
                            float(optArg), float(undef), C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
-    return _run("gen2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S)
+    return _run("gen2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices)
 
 
 def solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1Sqr, optArg,
                       undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
-                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False):
+                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False, devices=None):
     """Batched ``invert_standard_3D`` (numbas.py:15-212) over S[..., nz, ny, nx], in place."""
     ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("F", F)], 3)
     nz, ny, nx = ops.core
     tail = lambda fl, nb: (nb, nz, ny, nx, _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
                            float(delxSqr), float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
                            C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
-    return _run("std3d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S)
+    return _run("std3d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices)
 
 
 # ---------------------------------------------------------------------------
