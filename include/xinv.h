@@ -115,6 +115,10 @@ int  xinv_timer_stop(xinv_ctx *ctx, double *ms_out);   /* records, synchronises,
 /* pinned host memory helpers (so callers can stage at full PCIe rate) */
 int  xinv_host_alloc(void **out, int64_t bytes);
 int  xinv_host_free(void *p);
+/* *out = 1 if p lies in page-locked (cudaHostAlloc'ed / registered) memory, 0 for ordinary pageable memory:
+ * callers stage pageable inputs through their own pinned buffers (a copy from pageable memory runs at a
+ * fraction of the PCIe rate and cannot overlap) */
+int  xinv_host_is_pinned(const void *p, int *out);
 /* device memory helpers for callers without torch (bench / tests) */
 int  xinv_dev_alloc(xinv_ctx *ctx, void **out, int64_t bytes);
 int  xinv_dev_free(xinv_ctx *ctx, void *p);
@@ -205,6 +209,40 @@ int xinv_std3d(xinv_ctx *ctx, double *S, const double *A, const double *B,
                double delxSqr, double ratio2Sqr, double ratio1Sqr,
                double optArg, double undef, double *flags,
                int64_t mxLoop, double tolerance, const xinv_opts *opts);
+
+/* ---- epilogue: flow components from the inverted field ----------------------------------
+ * Replaces the array work of apps.cal_flow (apps.py:1181-1317): centred differences of S along
+ * the two core dimensions -- numpy.gradient's formulas, chosen by the caller exactly as numpy
+ * chooses them -- and the per-row combination of the 'GillMatsuno' branch (apps.py:1277-1317) or
+ * the metric division and signs of the 'streamfunction' / 'velocitypotential' branches
+ * (apps.py:1207-1271, finitediffs.py:151-207, :548-659).  All pointers follow opts->mem_space. */
+#define XINV_EDGE_ONESIDED 0  /* no padding: one-sided differences at the ends (numpy.gradient, edge_order 1) */
+#define XINV_EDGE_FIXED    1  /* padBCs 'fixed': the value beyond the end is lo / hi                              */
+#define XINV_EDGE_EXTEND   2  /* 'extend': the edge value                                                         */
+#define XINV_EDGE_REFLECT  3  /* 'reflect': the first inner value                                                 */
+#define XINV_EDGE_PERIODIC 4  /* 'periodic': the value from the other end                                         */
+#define XINV_FLOW_GRAD     0  /* out1 = s1 * (dS/dy / rows[0][j]), out2 = s2 * (dS/dx / rows[1][j]); swap: (x, y) */
+#define XINV_FLOW_GM_LL    1  /* Gill-Matsuno lat-lon: rows = coef1, coef2, cosLat                                */
+#define XINV_FLOW_GM_CART  2  /* Gill-Matsuno cartesian: rows = coef1, coef2                                      */
+typedef struct xinv_flow_axis {
+    int32_t uniform;          /* 1: (f[i+1] - f[i-1]) / den;  0: w[0][i] f[i-1] + w[1][i] f[i] + w[2][i] f[i+1]   */
+    int32_t edge;             /* XINV_EDGE_*                                                                      */
+    double den;               /* uniform: 2 dx                                                                    */
+    double lo, hi;            /* ONESIDED: spacing of the one-sided differences; FIXED: the fill values           */
+    const double *w;          /* non-uniform: [3][n]                                                              */
+} xinv_flow_axis;
+typedef struct xinv_flow_desc {
+    int32_t struct_size;      /* = sizeof(xinv_flow_desc)                                                         */
+    int32_t comb;             /* XINV_FLOW_*                                                                      */
+    int32_t swap;             /* GRAD: 1 = return (x-derivative, y-derivative)                                    */
+    int32_t nrows;            /* rows of `rows` (2 or 3)                                                          */
+    double s1, s2;            /* GRAD: +1 / -1                                                                    */
+    double deg2m;             /* GM_LL                                                                            */
+    xinv_flow_axis y, x;
+    const double *rows;       /* [nrows][ny]                                                                      */
+} xinv_flow_desc;
+int xinv_flow2d(xinv_ctx *ctx, double *out1, double *out2, const double *S,
+                int64_t batch, int64_t ny, int64_t nx, const xinv_flow_desc *desc, const xinv_opts *opts);
 
 /* ---- stepwise protocol (used by the multi-GPU driver so that ranks can
  *      exchange their active-slice counts between chunks of sweeps) ---------

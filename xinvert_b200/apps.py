@@ -140,48 +140,130 @@ def invert_omega(F, dims, coords='lat-lon', icbc=None,
 
 def cal_flow(S, dims, coords='lat-lon', BCs=['fixed', 'fixed'],
              vtype='streamfunction', mParams=default_mParams):
-    """Flow vector from the inverted field (apps.py:1181-1317).  Only the
-    ``vtype='GillMatsuno'`` branch (apps.py:1277-1317) is on the hot path and
-    implemented; the streamfunction / velocity-potential branches need the
-    reference's finite-difference toolkit."""
+    """Flow vector from the inverted field (apps.py:1181-1317): (u, v) from a streamfunction or a velocity
+    potential (centred differences with the boundary conditions padded on, divided by the metric;
+    apps.py:1207-1271, finitediffs.py:151-207, :548-659), or from the Gill-Matsuno mass field
+    (apps.py:1277-1317).
+
+    The array work runs on the device (``xinv_flow2d``: the same IEEE operations, in the order of the numpy
+    expressions the reference evaluates) when ``S`` is float64 with the two core dims last; otherwise -- and for
+    the 'z-lat' / 'z-lon' variants -- in numpy on the host (``_flow_host``), which gives the same bits."""
     if vtype.lower() not in ['streamfunction', 'velocitypotential', 'gillmatsuno']:
         raise Exception('unsupported vtype: ' + vtype + ', should be one of:\n' +
                         "['streamfunction', 'velocitypotential', 'gillmatsuno']")
-    if vtype != 'GillMatsuno':
-        raise NotImplementedError("cal_flow: only vtype='GillMatsuno' is provided by xinvert_b200")
-    mParams = _update(default_mParams, mParams, ['f0', 'beta', 'epsilon', 'Phi', 'Omega', 'Rearth'])
-    eps, f0, beta = mParams['epsilon'], mParams['f0'], mParams['beta']
-    Omega, Rearth = mParams['Omega'], mParams['Rearth']
-    sv = np.asarray(S.values, dtype=np.float64)
+    if len(dims) != 2:
+        raise Exception('2 dimensions are needed')
+    sv = np.asarray(S.values)
     ay, ax = list(S.dims).index(dims[0]), list(S.dims).index(dims[1])
-    ydef, xdef = coord_values(S, dims[0]), coord_values(S, dims[1])
-    # DataArray.differentiate == np.gradient along the coordinate (2nd order inside, 1st at the edges)
-    dSdy = np.gradient(sv, ydef, axis=ay, edge_order=1)
-    dSdx = np.gradient(sv, xdef, axis=ax, edge_order=1)
+    ydef = np.asarray(coord_values(S, dims[0]), dtype=np.float64)
+    xdef = np.asarray(coord_values(S, dims[1]), dtype=np.float64)
+    ny = ydef.size
+    c = coords.lower()
+    if vtype != 'GillMatsuno':                    # Poisson case
+        sf = (vtype == 'streamfunction')
+        R = 6371200.0                             # FiniteDiff's default radius (finitediffs.py:40)
+        deg2m = np.pi * R / 180.0
+        if c == 'lat-lon':
+            rows = np.stack([np.full(ny, deg2m), deg2m * np.cos(np.deg2rad(ydef))])
+        elif c == 'cartesian':
+            rows = np.ones((2, ny))
+        elif c in ('z-lat', 'z-lon'):
+            return _flow_zplane(S, sv, ay, ax, ydef, xdef, c, BCs, sf, deg2m)
+        else:
+            raise Exception('unsupported coords ' + coords + ', should be [lat-lon, z-lat, z-lon, cartesian]')
+        plan = dict(ydiff=_device_solvers.axis_diff(ydef, BCs[0]), xdiff=_device_solvers.axis_diff(xdef, BCs[1]),
+                    comb=0, rows=rows, swap=not sf, signs=(-1.0, 1.0) if sf else (1.0, 1.0))
+        for b in BCs:
+            if b not in ('fixed', 'extend', 'reflect', 'periodic'):
+                raise Exception('unsupported BC: ' + str(BCs))
+    else:                                         # GillMatsuno case
+        mParams = _update(default_mParams, mParams, ['f0', 'beta', 'epsilon', 'Phi', 'Omega', 'Rearth'])
+        eps, f0, beta = mParams['epsilon'], mParams['f0'], mParams['beta']
+        Omega, Rearth = mParams['Omega'], mParams['Rearth']
+        # DataArray.differentiate == np.gradient along the coordinate (2nd order inside, 1st at the edges)
+        yd, xd = _device_solvers.axis_diff(ydef, None), _device_solvers.axis_diff(xdef, None)
+        if c == 'lat-lon':
+            lats = np.deg2rad(ydef)
+            f = 2.0 * Omega * np.sin(lats)
+            rows = np.stack([eps / (eps ** 2.0 + f ** 2.0), f / (eps ** 2.0 + f ** 2.0), np.cos(lats)])
+            plan = dict(ydiff=yd, xdiff=xd, comb=1, rows=rows, deg2m=np.deg2rad(1.0) * Rearth)
+        elif c == 'cartesian':
+            f = f0 + beta * ydef
+            rows = np.stack([eps / (eps ** 2.0 + f ** 2.0), f / (eps ** 2.0 + f ** 2.0)])
+            plan = dict(ydiff=yd, xdiff=xd, comb=2, rows=rows)
+        else:
+            raise Exception('unsupported coords ' + coords + ', should be [lat-lon, cartesian]')
+    trailing = (ay == sv.ndim - 2 and ax == sv.ndim - 1)
+    if trailing and sv.dtype == np.float64 and core.solvers is _device_solvers:
+        c1, c2 = _device_solvers.flow_2d(sv, **plan)
+    else:
+        c1, c2 = _flow_host(sv, ay, ax, ydef, xdef, **plan)
+    return wrap_like(S, c1), wrap_like(S, c2)
+
+
+def _np_diff(sv, coord, axis, d):
+    """numpy's own evaluation of what ``axis_diff`` describes: np.gradient of the (padded) array along ``axis``."""
+    if d["edge"] is None:
+        return np.gradient(sv, coord, axis=axis, edge_order=1)
+    pw = [(0, 0)] * sv.ndim
+    pw[axis] = (1, 1)
+    if d["edge"] == 'periodic':
+        p = np.pad(sv, pw, mode='wrap')
+    elif d["edge"] == 'fixed':
+        p = np.pad(sv, pw, mode='constant', constant_values=[(0, 0)] * axis + [(d["lo"], d["hi"])] + [(0, 0)] * (sv.ndim - axis - 1))
+    else:
+        p = np.pad(sv, pw, mode={'extend': 'edge', 'reflect': 'reflect'}[d["edge"]])
+    x = np.concatenate([[0.0], np.asarray(coord, dtype=np.float64), [0.0]])
+    x[0] = x[1] * 2 - x[2]
+    x[-1] = x[-2] * 2 - x[-3]
+    g = np.gradient(p, x, axis=axis, edge_order=1)
+    sl = [slice(None)] * sv.ndim
+    sl[axis] = slice(1, -1)
+    return g[tuple(sl)]
+
+
+def _flow_host(sv, ay, ax, ydef, xdef, ydiff, xdiff, comb, rows, swap=False, signs=(1.0, 1.0), deg2m=1.0):
+    """The host (numpy) evaluation of cal_flow's array work: the expressions of apps.py:1207-1317 as they stand."""
+    sv = np.asarray(sv, dtype=np.float64)
+    dSdy = _np_diff(sv, ydef, ay, ydiff)
+    dSdx = _np_diff(sv, xdef, ax, xdiff)
 
     def along_y(v):                               # broadcast a function of dims[0] against S
         shp = [1] * sv.ndim
         shp[ay] = -1
         return np.reshape(v, shp)
 
-    if coords.lower() == 'lat-lon':
-        lats = np.deg2rad(ydef)
-        cosLat, sinLat = along_y(np.cos(lats)), along_y(np.sin(lats))
-        f = 2.0 * Omega * sinLat
-        deg2m = np.deg2rad(1.0) * Rearth
-        coef1 = eps / (eps ** 2.0 + f ** 2.0)
-        coef2 = f / (eps ** 2.0 + f ** 2.0)
+    if comb == 0:
+        gy, gx = dSdy / along_y(rows[0]), dSdx / along_y(rows[1])
+        r1, r2 = (gx, gy) if swap else (gy, gx)
+        return (-r1 if signs[0] < 0 else r1), (-r2 if signs[1] < 0 else r2)
+    coef1, coef2 = along_y(rows[0]), along_y(rows[1])
+    if comb == 1:
+        cosLat = along_y(rows[2])
         c1 = - coef1 * dSdx / deg2m / cosLat - coef2 * dSdy / deg2m
         c2 = - coef1 * dSdy / deg2m + coef2 * dSdx / deg2m / cosLat
-    elif coords.lower() == 'cartesian':
-        f = along_y(f0 + beta * ydef)
-        coef1 = eps / (eps ** 2.0 + f ** 2.0)
-        coef2 = f / (eps ** 2.0 + f ** 2.0)
+    else:
         c1 = - coef1 * dSdx - coef2 * dSdy
         c2 = - coef1 * dSdy + coef2 * dSdx
+    return c1, c2
+
+
+def _flow_zplane(S, sv, ay, ax, ydef, xdef, c, BCs, sf, deg2m):
+    """The 'z-lat' / 'z-lon' variants of the streamfunction / velocity-potential branch (apps.py:1225-1256), numpy."""
+    sv = np.asarray(sv, dtype=np.float64)
+    d0, d1 = _device_solvers.axis_diff(ydef, BCs[0]), _device_solvers.axis_diff(xdef, BCs[1])
+    g0 = _np_diff(sv, ydef, ay, d0)               # d/dz: scale 1
+    g1 = _np_diff(sv, xdef, ax, d1) / deg2m       # d/dlat or d/dlon with no latitude dimension: scale deg2m (cos = 1)
+    if c == 'z-lat':
+        shp = [1] * sv.ndim
+        shp[ax] = -1
+        cos = np.reshape(np.cos(np.deg2rad(xdef)), shp)
+        g0, g1 = g0 / cos, g1 / cos
+        g1 = np.where(np.reshape(np.abs(xdef), shp) != 90, g1, 0)
+        r = (-g0, g1) if sf else (g1, g0)
     else:
-        raise Exception('unsupported coords ' + coords + ', should be [lat-lon, cartesian]')
-    return wrap_like(S, c1), wrap_like(S, c2)
+        r = (g0, -g1) if sf else (g1, g0)
+    return wrap_like(S, r[0]), wrap_like(S, r[1])
 
 
 # ---------------------------------------------------------------------------

@@ -24,6 +24,7 @@
 #include "xinv_march2d.cuh"
 #include "xinv_march3d.cuh"
 #include "xinv_lex_engine.cuh"
+#include "xinv_flow.cuh"
 
 // ---------------------------------------------------------------------------
 // errors
@@ -239,6 +240,15 @@ extern "C" int xinv_host_alloc(void **out, int64_t bytes)
 extern "C" int xinv_host_free(void *p)
 {
     if (p) CK(cudaFreeHost(p));
+    return XINV_OK;
+}
+extern "C" int xinv_host_is_pinned(const void *p, int *out)
+{
+    if (!out) return set_err(XINV_E_ARG, "out is NULL");
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); *out = 0; return XINV_OK; }
+    *out = (at.type == cudaMemoryTypeHost) ? 1 : 0;
     return XINV_OK;
 }
 extern "C" int xinv_dev_alloc(xinv_ctx *c, void **out, int64_t bytes)
@@ -977,6 +987,83 @@ extern "C" int xinv_std3d(xinv_ctx *ctx, double *S, const double *A, const doubl
                               ratio1Sqr, optArg, undef, flags, mxLoop, tolerance, opts);
     if (rc) return rc;
     return run_to_completion(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// cal_flow epilogue
+// ---------------------------------------------------------------------------
+extern "C" int xinv_flow2d(xinv_ctx *c, double *out1, double *out2, const double *S,
+                           int64_t batch, int64_t ny, int64_t nx, const xinv_flow_desc *d, const xinv_opts *opts)
+{
+    if (!c || !out1 || !out2 || !S || !d) return set_err(XINV_E_ARG, "NULL argument");
+    if (d->struct_size != (int32_t)sizeof(xinv_flow_desc)) return set_err(XINV_E_ARG, "desc.struct_size %d != %zu", d->struct_size, sizeof(xinv_flow_desc));
+    if (batch < 0 || batch > 65535 || ny < 2 || nx < 2) return set_err(XINV_E_ARG, "bad sizes batch=%lld ny=%lld nx=%lld", (long long)batch, (long long)ny, (long long)nx);
+    if (d->comb < XINV_FLOW_GRAD || d->comb > XINV_FLOW_GM_CART) return set_err(XINV_E_ARG, "bad comb");
+    const int need_rows = (d->comb == XINV_FLOW_GM_LL) ? 3 : 2;
+    if (!d->rows || d->nrows != need_rows) return set_err(XINV_E_ARG, "rows: %d vectors needed", need_rows);
+    const xinv_flow_axis *axs[2] = {&d->y, &d->x};
+    const int64_t len[2] = {ny, nx};
+    for (int m = 0; m < 2; ++m) {
+        if (axs[m]->edge < XINV_EDGE_ONESIDED || axs[m]->edge > XINV_EDGE_PERIODIC) return set_err(XINV_E_ARG, "bad edge code");
+        if (!axs[m]->uniform && !axs[m]->w) return set_err(XINV_E_ARG, "non-uniform axis without weights");
+    }
+    int mem = XINV_MEM_HOST;
+    if (opts) {
+        if (opts->struct_size != (int32_t)sizeof(xinv_opts)) return set_err(XINV_E_ARG, "opts.struct_size");
+        mem = opts->mem_space;
+    }
+    CK(cudaSetDevice(c->device));
+    memset(&c->stats, 0, sizeof c->stats);
+    if (batch == 0) return XINV_OK;
+    const size_t bytes = sizeof(double) * (size_t)batch * ny * nx;
+    XfArgs a{};
+    a.ny = ny; a.nx = nx; a.comb = d->comb; a.swap = d->swap; a.s1 = d->s1; a.s2 = d->s2; a.deg2m = d->deg2m;
+    const double *dS = S;
+    double *d1 = out1, *d2 = out2;
+    int rc;
+    // small operands: rows | y weights | x weights in one staging buffer
+    const size_t nsmall = (size_t)need_rows * ny + 3 * (size_t)ny + 3 * (size_t)nx;
+    if ((rc = ensure(c->stage[3], sizeof(double) * nsmall))) return rc;
+    double *sm = (double *)c->stage[3].p;
+    const cudaMemcpyKind kin = (mem == XINV_MEM_HOST) ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(sm, d->rows, sizeof(double) * need_rows * ny, kin, c->stream));
+    a.rows = sm;
+    double *wp = sm + (size_t)need_rows * ny;
+    XfAxis *dst[2] = {&a.y, &a.x};
+    for (int m = 0; m < 2; ++m) {
+        dst[m]->uniform = axs[m]->uniform; dst[m]->edge = axs[m]->edge; dst[m]->den = axs[m]->den;
+        dst[m]->lo = axs[m]->lo; dst[m]->hi = axs[m]->hi; dst[m]->w = nullptr;
+        if (!axs[m]->uniform) {
+            CK(cudaMemcpyAsync(wp, axs[m]->w, sizeof(double) * 3 * len[m], kin, c->stream));
+            dst[m]->w = wp;
+        }
+        wp += 3 * len[m];
+    }
+    if (mem == XINV_MEM_HOST) {
+        if ((rc = ensure(c->stage[0], bytes))) return rc;
+        if ((rc = ensure(c->stage[1], bytes))) return rc;
+        if ((rc = ensure(c->stage[2], bytes))) return rc;
+        CK(cudaMemcpyAsync(c->stage[0].p, S, bytes, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes = (i64)bytes;
+        dS = (const double *)c->stage[0].p; d1 = (double *)c->stage[1].p; d2 = (double *)c->stage[2].p;
+    }
+    if (ny > 65535) return set_err(XINV_E_ARG, "ny > 65535");
+    dim3 grid((unsigned)((nx + 127) / 128), (unsigned)ny, (unsigned)batch);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    xf_flow2d_kernel<<<grid, 128, 0, c->stream>>>(d1, d2, dS, a);
+    c->stats.kernel_launches = 1;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if (mem == XINV_MEM_HOST) {
+        CK(cudaMemcpyAsync(out1, d1, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(out2, d2, bytes, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes = (i64)(2 * bytes);
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.solve_ms = ms;
+    return XINV_OK;
 }
 
 // ---------------------------------------------------------------------------

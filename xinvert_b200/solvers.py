@@ -157,7 +157,7 @@ def _sync_torch_stream(device_array):
 # two sets of staging buffers): while one chunk is being solved the next one is copied to the device and the
 # previous result is copied back.  Every slice still stops on its own test; results do not depend on the cut.
 # ---------------------------------------------------------------------------
-PIPE_MIN_CELLS = 4 << 20          # a chunk keeps at least this many cells (enough work to fill the GPU)
+PIPE_MIN_CELLS = 8 << 20          # a chunk keeps at least this many cells (the fused kernels lose efficiency below)
 PIPE_STREAMS = 2
 
 
@@ -176,7 +176,7 @@ def _plan(batch, cells_per_slice, devices, pipelined):
             nchunk = max(1, min(n, (n * cells_per_slice) // PIPE_MIN_CELLS))
             if nchunk > 1:
                 nchunk = max(nchunk, PIPE_STREAMS)
-            nchunk = min(nchunk, 4 * PIPE_STREAMS)          # a few chunks are enough to hide the copies
+            nchunk = min(nchunk, 2 * PIPE_STREAMS)          # a few chunks are enough to hide the copies
         nchunk = max(nchunk, -(-n // MAX_BATCH))
         for k in range(nchunk):
             clo, chi = shard_bounds(n, nchunk, k)
@@ -322,11 +322,17 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
         if v is not None and tuple(v.shape) != (ny,):
             raise ValueError(f"{name} must have shape ({ny},)")
     fl = _flags_array(flags, batch)
+    stage_F = (not device) and not _lib.is_pinned(Fh)      # pageable forcing: through pinned buffers, chunk by chunk
 
     def call(c, lo, hi):
         opts = _lib.make_opts(mem_space=_lib.MEM_DEVICE if device else _lib.MEM_HOST, check_every=check_every)
         off = lambda p: C.c_void_p(p.value + 8 * lo * ny * nx)
-        rc = L.xinv_std2d_rows(c.handle, off(S_ptr), ptr(rows[0]), ptr(rows[1]), off(F_ptr), ptr(rows[2]),
+        Fc = off(F_ptr)
+        if stage_F and hi > lo:
+            buf = _lib.pinned_empty((hi - lo, ny, nx))      # pooled; filled by a few threads while the other chunk solves
+            _lib.parallel_copy(buf, Fh.reshape(batch, ny, nx)[lo:hi])
+            Fc = C.c_void_p(buf.ctypes.data)
+        rc = L.xinv_std2d_rows(c.handle, off(S_ptr), ptr(rows[0]), ptr(rows[1]), Fc, ptr(rows[2]),
                                float(user_undef), float(out_undef), hi - lo, ny, nx, _lib.BC_CODES[BCy],
                                _lib.BC_CODES[BCx], float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg),
                                float(undef), C.c_void_p(fl[lo:hi].ctypes.data), int(mxLoop), float(tolerance),
@@ -440,6 +446,76 @@ def solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1S
                            float(delxSqr), float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
                            C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
     return _run("std3d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices)
+
+
+# ---------------------------------------------------------------------------
+# cal_flow epilogue (xinv_flow2d)
+# ---------------------------------------------------------------------------
+def axis_diff(coord, edge=None, fill=(0.0, 0.0)):
+    """How ``numpy.gradient`` differentiates along an axis with these coordinate values -- decided here exactly as
+    numpy decides it -- for an unpadded line (``edge=None``: DataArray.differentiate, one-sided ends) or for the line
+    padded by finitediffs.padBCs (``edge`` in fixed / extend / reflect / periodic; finitediffs.py:548-606: the two
+    extra coordinate values are linear extrapolations).  Returns a dict for ``flow_2d``."""
+    x = np.asarray(coord, dtype=np.float64)
+    n = x.size
+    if edge is not None:
+        x = np.concatenate([[0.0], x, [0.0]])
+        x[0] = x[1] * 2 - x[2]
+        x[-1] = x[-2] * 2 - x[-3]
+    dx = np.diff(x)
+    uniform = bool((dx == dx[0]).all())
+    d = dict(uniform=uniform, edge=edge, den=2. * dx[0], lo=float(dx[0]), hi=float(dx[-1]), w=None)
+    if edge == "fixed":
+        d["lo"], d["hi"] = float(fill[0]), float(fill[1])
+    if not uniform:
+        dx1, dx2 = dx[0:-1], dx[1:]
+        a = -(dx2) / (dx1 * (dx1 + dx2))
+        b = (dx2 - dx1) / (dx1 * dx2)
+        c = dx1 / (dx2 * (dx1 + dx2))
+        w = np.zeros((3, n))
+        sl = slice(1, n - 1) if edge is None else slice(0, n)
+        w[0, sl], w[1, sl], w[2, sl] = a, b, c
+        d["w"] = w
+    return d
+
+
+def flow_2d(S, ydiff, xdiff, comb, rows, swap=False, signs=(1.0, 1.0), deg2m=1.0, ctx=None):
+    """Two flow components from ``S[..., ny, nx]`` (host float64) on the device: centred differences along the last
+    two axes as described by ``axis_diff`` and the combination ``comb`` of include/xinv.h (XINV_FLOW_*)."""
+    L = _lib.load()
+    ctx = ctx or _lib.default_context()
+    Sh = _host_f64(S, "S")
+    shape = Sh.shape
+    ny, nx = int(shape[-2]), int(shape[-1])
+    batch = int(np.prod(shape[:-2], dtype=np.int64)) if len(shape) > 2 else 1
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    o1, o2 = _lib.pinned_empty(shape), _lib.pinned_empty(shape)
+    keep = []
+
+    def axis(d):
+        ax = _lib.XinvFlowAxis()
+        ax.uniform, ax.edge, ax.den, ax.lo, ax.hi = int(d["uniform"]), _lib.EDGE_CODES[d["edge"]], d["den"], d["lo"], d["hi"]
+        if d["w"] is not None:
+            w = np.ascontiguousarray(d["w"], dtype=np.float64)
+            keep.append(w)
+            ax.w = w.ctypes.data
+        return ax
+
+    desc = _lib.XinvFlowDesc()
+    desc.struct_size = C.sizeof(_lib.XinvFlowDesc)
+    desc.comb, desc.swap, desc.nrows = int(comb), int(bool(swap)), int(rows.shape[0])
+    desc.s1, desc.s2, desc.deg2m = float(signs[0]), float(signs[1]), float(deg2m)
+    desc.y, desc.x = axis(ydiff), axis(xdiff)
+    desc.rows = rows.ctypes.data
+    opts = _lib.make_opts(mem_space=_lib.MEM_HOST)
+    N = ny * nx
+    with ctx.lock:
+        for lo, hi in _batch_chunks(batch):
+            o = 8 * lo * N
+            _lib.check(L.xinv_flow2d(ctx.handle, C.c_void_p(o1.ctypes.data + o), C.c_void_p(o2.ctypes.data + o),
+                                     C.c_void_p(Sh.ctypes.data + o), hi - lo, ny, nx, C.byref(desc), C.byref(opts)))
+    del keep
+    return o1, o2
 
 
 # ---------------------------------------------------------------------------
