@@ -50,7 +50,7 @@ def test_pipelined_dense_general_form_and_3d(gpu_ctx, monkeypatch):
     S1, S2 = c["S0"].copy(), c["S0"].copy()
     f1, st1 = xb.solve_general_2D(S1, c["A"], None, c["C"], c["D"], c["E"], c["F"], c["G"], *args, mxLoop=300, tolerance=1e-6, ctx=gpu_ctx)
     f2, st2 = xb.solve_general_2D(S2, c["A"], None, c["C"], c["D"], c["E"], c["F"], c["G"], *args, mxLoop=300, tolerance=1e-6)
-    assert np.array_equal(S1, S2) and np.array_equal(f1, f2) and st2["pipeline"]["chunks"] == 6
+    assert np.array_equal(S1, S2) and np.array_equal(f1, f2) and st2["pipeline"]["chunks"] == 2 * solvers.PIPE_STREAMS
     c = cases.random_std3d(6, 20, 64, seed=3, batch=4)
     p = c["p"]
     args = ("fixed", "extend", "periodic", p["del1Sqr"], p["ratio2Sqr"], p["ratio1Sqr"], p["optArg"], cases.UNDEF)

@@ -405,14 +405,24 @@ def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, 
     S = _lib.pinned_empty(shape)
     fl = _flags_array(flags, batch)
     N = nz * ny * nx
+    stage_F = not _lib.is_pinned(Fh)             # pageable operands: through pinned buffers (parallel copies)
+    if n2.size * 8 >= (8 << 20) and not _lib.is_pinned(n2):
+        n2p = _lib.pinned_empty(n2.shape)
+        _lib.parallel_copy(n2p, n2)
+        n2 = n2p
 
     def call(c, lo, hi):
         opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
         o = 8 * lo * N
         n2_off = 8 * lo * int(n2_strides[0])
+        Fc = Fh.ctypes.data + o
+        if stage_F and hi > lo:
+            buf = _lib.pinned_empty((hi - lo, nz, ny, nx))
+            _lib.parallel_copy(buf, Fh.reshape(batch, nz, ny, nx)[lo:hi])
+            Fc = buf.ctypes.data
         rc = L.xinv_std3d_rows(c.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
                                C.c_void_p(n2.ctypes.data + n2_off), st4, int(n2.size - lo * int(n2_strides[0])),
-                               C.c_void_p(Fh.ctypes.data + o), float(user_undef), float(out_undef), hi - lo, nz, ny, nx,
+                               C.c_void_p(Fc), float(user_undef), float(out_undef), hi - lo, nz, ny, nx,
                                _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delxSqr),
                                float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
                                C.c_void_p(fl[lo:hi].ctypes.data), int(mxLoop), float(tolerance), C.byref(opts))
