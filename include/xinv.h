@@ -52,6 +52,8 @@ extern "C" {
 #define XINV_ENGINE_AUTO    0
 #define XINV_ENGINE_COLOUR  1 /* one in-place kernel per colour + fused norm/decide     */
 #define XINV_ENGINE_FUSED   2 /* TMA-staged fused red+black iteration kernel (2-D, B==0)*/
+#define XINV_ENGINE_RESIDENT 3 /* small 2-D slices: the whole solve in one CTA, operands in shared memory */
+#define XINV_ENGINE_CLUSTER 4 /* 2-D, B==0, row coefficients: the whole solve in one thread-block cluster (psi in registers + DSMEM) */
 
 /* error codes */
 #define XINV_OK          0

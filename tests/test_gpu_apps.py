@@ -182,7 +182,8 @@ def test_stommel_ishida_reference_known_answers(gpu_ctx, capsys):
 
 
 def test_eliassen_nine_point_bit_exact_vs_oracle(gpu_ctx):
-    """invert_Eliassen (B != 0: 9-point stencil, 4-colour ordering on the colour engine)."""
+    """invert_Eliassen (B != 0: 9-point stencil, 4-colour ordering; a z-r section of this size runs
+    on the resident engine -- the whole solve in one CTA -- a larger one on the colour engine)."""
     ny, nx = 60, 90
     z, y = np.linspace(1000., 100., ny), np.linspace(0., 5e5, nx)
     coords = {'z': z, 'r': y}
@@ -195,7 +196,7 @@ def test_eliassen_nine_point_bit_exact_vs_oracle(gpu_ctx):
     kw = dict(dims=['z', 'r'], coords='cartesian', iParams=ip, mParams={'A': A, 'B': B, 'C': C})
     s_g = xb.invert_Eliassen(F, **kw)
     st = xb.default_context().stats()
-    assert st["engine"] == "colour" and st["ncolours"] == 4
+    assert st["engine"] == "resident" and st["ncolours"] == 4
     s_o = _via_oracle(xb.invert_Eliassen, F, **kw)
     assert np.array_equal(s_g.values, s_o.values)
 

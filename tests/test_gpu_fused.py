@@ -130,6 +130,11 @@ def test_fused_odd_nx_periodic_falls_back_to_colour_engine(gpu_ctx):
     S_o, _ = cases.run_std2d(oracle, c, "fixed", "periodic", 3, -1.0, ordering="colour")
     S_g, _ = cases.run_std2d(xb, c, "fixed", "periodic", 3, -1.0, engine="auto")
     assert np.array_equal(S_g, S_o)
+    assert xb.default_context().stats()["engine"] == "resident"      # small enough for one SM's shared memory
+    c = cases.random_std2d(120, 131, with_B=False, seed=1)
+    S_o, _ = cases.run_std2d(oracle, c, "fixed", "periodic", 3, -1.0, ordering="colour")
+    S_g, _ = cases.run_std2d(xb, c, "fixed", "periodic", 3, -1.0, engine="auto")
+    assert np.array_equal(S_g, S_o)
     assert xb.default_context().stats()["engine"] == "colour"
 
 

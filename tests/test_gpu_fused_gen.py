@@ -55,7 +55,7 @@ def test_fused_gen2d_to_tolerance_and_auto_engine(gpu_ctx):
 
 
 def test_gen2d_x_varying_coefficients_stay_on_colour_engine(gpu_ctx):
-    c = cases.random_gen2d(40, 64, with_B=False, seed=5)
+    c = cases.random_gen2d(80, 128, with_B=False, seed=5)
     with pytest.raises(xb.XinvError):
         cases.run_gen2d(xb, c, "fixed", "periodic", 3, -1.0, engine="fused")
     S_o, f_o = cases.run_gen2d(oracle, c, "fixed", "periodic", 3, -1.0, ordering="colour")

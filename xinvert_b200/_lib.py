@@ -15,8 +15,8 @@ from . import build as _build
 BC_CODES = {"fixed": 0, "extend": 1, "periodic": 2}
 ORDER_CODES = {"colour": 0, "color": 0, "redblack": 0, "red-black": 0,
                "lexicographic": 1, "lex": 1}
-ENGINE_CODES = {"auto": 0, "colour": 1, "color": 1, "fused": 2}
-ENGINE_NAMES = {0: "auto", 1: "colour", 2: "fused"}
+ENGINE_CODES = {"auto": 0, "colour": 1, "color": 1, "fused": 2, "resident": 3, "cluster": 4}
+ENGINE_NAMES = {0: "auto", 1: "colour", 2: "fused", 3: "resident", 4: "cluster"}
 MEM_HOST, MEM_DEVICE = 0, 1
 
 

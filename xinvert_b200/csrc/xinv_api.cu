@@ -25,6 +25,8 @@
 #include "xinv_march3d.cuh"
 #include "xinv_lex_engine.cuh"
 #include "xinv_flow.cuh"
+#include "xinv_resident.cuh"
+#include "xinv_cluster2d.cuh"
 
 // ---------------------------------------------------------------------------
 // errors
@@ -80,6 +82,8 @@ struct Problem {
     int h_nactive = 0;
     FusedPlan fused{};
     Fused3Plan fused3{};         // 3-D standard form (xinv_march3d.cuh)
+    ResidentPlan resident{};     // small 2-D slices (xinv_resident.cuh)
+    ClusterPlan cluster{};       // small / medium 2-D slices with row coefficients, on top of `fused` (xinv_cluster2d.cuh)
     bool front = false;          // xinv_std2d_rows: S is output only, de-masked on the device
 };
 
@@ -362,6 +366,8 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     Problem &pb = c->pb;
     fused_plan_release(pb.fused);
     fused3_plan_release(pb.fused3);
+    resident_plan_release(pb.resident);
+    cluster_plan_release(pb.cluster);
     pb = Problem();
     pb.kind = a.kind;
     pb.batch = a.batch;
@@ -537,8 +543,16 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
 
     // ---- engine choice ----------------------------------------------------
     pb.engine = XINV_ENGINE_COLOUR;
-    if (pb.ordering == XINV_ORDER_COLOUR && o.engine != XINV_ENGINE_COLOUR) {
+    if (o.engine == XINV_ENGINE_RESIDENT) {
         std::string why;
+        if (pb.ordering != XINV_ORDER_COLOUR || a.front) why = "needs the colour ordering and dense operands";
+        else if (resident_plan_build(pb.resident, c->sm_count, pb.kind, pb.hasB, g, pb.q, pb.batch, pb.dS, why) == 0)
+            pb.engine = XINV_ENGINE_RESIDENT;
+        if (pb.engine != XINV_ENGINE_RESIDENT)
+            return set_err(XINV_E_UNSUPPORTED, "resident engine unavailable: %s", why.c_str());
+    } else if (pb.ordering == XINV_ORDER_COLOUR && o.engine != XINV_ENGINE_COLOUR) {
+        std::string why;
+        if (o.engine == XINV_ENGINE_CLUSTER && pb.kind == XD_STD3D) return set_err(XINV_E_UNSUPPORTED, "cluster engine: 2-D problems only");
         if (pb.kind == XD_STD3D) {
             const char *e3 = getenv("XINV_FUSED3");
             if (e3 && atoi(e3) == 0) why = "disabled by XINV_FUSED3=0";
@@ -552,10 +566,28 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
             rc = fused_plan_build(pb.fused, c->xm_work, c->sm_count, pb.kind, g, pb.q, pb.batch, pb.dS, pb.mxLoop, c->stream, why,
                                   a.front ? &front : nullptr);
             if (rc == 0) pb.engine = XINV_ENGINE_FUSED;
-            else if (o.engine == XINV_ENGINE_FUSED || a.front)
+            else if (o.engine == XINV_ENGINE_FUSED || o.engine == XINV_ENGINE_CLUSTER || a.front)
                 return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
-        } else if (o.engine == XINV_ENGINE_FUSED) {
+            // slices that fit a thread-block cluster stay on the SMs for the whole solve (same operands, xinv_cluster2d.cuh)
+            if (rc == 0 && (o.engine == XINV_ENGINE_AUTO || o.engine == XINV_ENGINE_CLUSTER)) {
+                const char *ec = getenv("XINV_CLUSTER");
+                std::string whyc = "disabled by XINV_CLUSTER=0";
+                if (!(ec && atoi(ec) == 0 && o.engine == XINV_ENGINE_AUTO))
+                    cluster_plan_build(pb.cluster, pb.fused, c->sm_count, g, pb.q, pb.batch, whyc);
+                if (!pb.cluster.built && o.engine == XINV_ENGINE_CLUSTER)
+                    return set_err(XINV_E_UNSUPPORTED, "cluster engine unavailable: %s", whyc.c_str());
+            }
+        } else if (o.engine == XINV_ENGINE_FUSED || o.engine == XINV_ENGINE_CLUSTER) {
             return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
+        }
+        // what the fused engines do not take (9-point stencil, x-varying general form, odd nx with periodic-x):
+        // small slices go to the resident engine instead of the launch-bound colour engine
+        if (pb.engine == XINV_ENGINE_COLOUR && o.engine == XINV_ENGINE_AUTO && !a.front && pb.kind != XD_STD3D) {
+            const char *er = getenv("XINV_RESIDENT");
+            std::string why2;
+            if (!(er && atoi(er) == 0) &&
+                resident_plan_build(pb.resident, c->sm_count, pb.kind, pb.hasB, g, pb.q, pb.batch, pb.dS, why2) == 0)
+                pb.engine = XINV_ENGINE_RESIDENT;
         }
     }
     {
@@ -593,8 +625,8 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     }
     pb.h_nactive = (int)a.batch;
 
-    c->stats.engine = pb.engine;
-    c->stats.iters_per_pass = (pb.engine == XINV_ENGINE_FUSED && pb.fused.built) ? pb.fused.T : 1;
+    c->stats.engine = pb.cluster.built ? XINV_ENGINE_CLUSTER : pb.engine;
+    c->stats.iters_per_pass = (pb.engine == XINV_ENGINE_FUSED && pb.fused.built && !pb.cluster.built) ? pb.fused.T : 1;
     c->stats.row_coeffs = (pb.engine == XINV_ENGINE_FUSED && ((pb.fused.built && pb.fused.rc) || (pb.fused3.built && pb.fused3.arow))) ? 1 : 0;
     pb.open = true;
     return XINV_OK;
@@ -675,6 +707,9 @@ static int sweep_colour_engine(xinv_ctx *c, Problem &pb)
 static int auto_check_every(const xinv_ctx *c, const Problem &pb)
 {
     if (pb.check_every > 0) return pb.check_every;
+    // resident engine: a launch iterates inside the SM until its slices stop; the budget only bounds
+    // how long a launch may run (operands are staged again by the next one)
+    if (pb.engine == XINV_ENGINE_RESIDENT || pb.cluster.built) return 4096;
     // Aim at ~6 ms of device work between host polls of the active count.  Passes launched
     // after every slice has stopped find nothing to do (a few microseconds each), so polling
     // rarely costs little; polling often costs a stream synchronisation per poll (measured on
@@ -698,7 +733,7 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
     // a pass (launch) performs >= 1 sweep on every active slice, except for at most one
     // "redo" pass per slice (fused engine, T > 1): at most mxLoop + 2 passes (numbas.py:410)
     const bool f3 = (pb.engine == XINV_ENGINE_FUSED && pb.fused3.built);
-    const i64 max_passes = pb.mxLoop + 1 + ((pb.engine == XINV_ENGINE_FUSED && !f3 && pb.fused.T > 1) ? 1 : 0);
+    const i64 max_passes = pb.mxLoop + 1 + ((pb.engine == XINV_ENGINE_FUSED && !f3 && !pb.cluster.built && pb.fused.T > 1) ? 1 : 0);
     const i64 remaining = max_passes - pb.sweeps_launched;
     if (sweeps <= 0) sweeps = auto_check_every(c, pb);
     if (sweeps > remaining) sweeps = remaining;
@@ -710,7 +745,17 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
             rc = lex_sweep(c->stream, pb.kind, pb.hasB, pb.g, pb.q, pb.batch, pb.dS, (XdSliceState *)c->state.p,
                            pb.nblk_norm, (double *)c->psum.p, (i64 *)c->pcnt.p, (unsigned *)c->ticket.p,
                            (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit, &c->stats.kernel_launches);
-        else if (f3) {
+        else if (pb.engine == XINV_ENGINE_RESIDENT) {
+            did = sweeps - it;                                                   // the whole chunk in one launch
+            rc = resident_sweep(pb.resident, c->stream, (XdSliceState *)c->state.p, (int *)c->nactive.p, pb.tol, pb.mxLoop,
+                                pb.zero_exit, (int)did, &c->stats.kernel_launches);
+            if (rc) return set_err(XINV_E_CUDA, "resident engine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else if (pb.cluster.built) {
+            did = sweeps - it;                                                   // the whole chunk in one launch
+            rc = cluster_sweep(pb.cluster, c->stream, (XdSliceState *)c->state.p, (int *)c->nactive.p, pb.tol, pb.mxLoop,
+                               pb.zero_exit, (int)did, &c->stats.kernel_launches);
+            if (rc) return set_err(XINV_E_CUDA, "cluster engine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else if (f3) {
             did = sweeps - it < pb.fused3.ppl ? sweeps - it : pb.fused3.ppl;     // passes in this launch
             rc = fused3_sweep(pb.fused3, c->stream, (XdSliceState *)c->state.p, (double *)c->psum.p, (i64 *)c->pcnt.p,
                               (unsigned *)c->ticket.p, (int *)c->nactive.p, pb.tol, pb.mxLoop, (int)did,
@@ -799,10 +844,12 @@ extern "C" int xinv_end(xinv_ctx *c)
     } else if (pb.profile && pb.engine == XINV_ENGINE_FUSED && pb.ordering != XINV_ORDER_LEX && pb.fused.T > 0) {
         // passes that did work: the chunks were timed as a whole and may end with passes that found every
         // slice stopped (a few microseconds each, left in dom_ms); count only the real ones
-        c->stats.dom_launches = (max_done + pb.fused.T - 1) / pb.fused.T;
+        c->stats.dom_launches = pb.cluster.built ? max_done : (max_done + pb.fused.T - 1) / pb.fused.T;   // cluster engine: per sweep
     }
     fused_plan_release(pb.fused);
     fused3_plan_release(pb.fused3);
+    resident_plan_release(pb.resident);
+    cluster_plan_release(pb.cluster);
     return XINV_OK;
 }
 

@@ -1,0 +1,449 @@
+// xinv_cluster2d.cuh -- XINV_ENGINE_CLUSTER: the whole solve of a small or medium 2-D slice inside
+// ONE THREAD-BLOCK CLUSTER, psi resident in registers and distributed shared memory.
+//
+// For slices of up to ~10^5 cells (BASELINE configs[0], 360 x 180; reanalysis-sized 144 x 73 ...)
+// the marching engine (xinv_march2d.cuh) is bound by its fixed cost per pass -- a grid-wide barrier,
+// the final reduction, the pipeline refill: 4.8 us per sweep on 360 x 180 where the arithmetic needs
+// a fraction of a microsecond.  Here the slice never leaves the SMs between sweeps:
+//   * the rows of the slice are dealt out to the R CTAs of a cluster (R = 1, 2, 4, 8 or 16), a row to
+//     WPR warps, a run of K consecutive cells to a thread;
+//   * a thread keeps psi and Fd (general form: Gm) of its K cells IN REGISTERS for the whole solve,
+//     together with the row values A[j], A[j+1], C[j], fac[j] (general form: A, C, D, E, F, fac):
+//     the east/west neighbours of a cell are registers of the same thread, only the first and last
+//     cell of the run look into the neighbouring thread's run;
+//   * updated values are published to a shared-memory tile of the CTA's rows (+ one halo row above
+//     and below) for the north/south neighbours; a value in the first / last row of a CTA is also
+//     pushed straight into the halo row of the neighbouring CTA's tile through distributed shared
+//     memory (st to a mapa-translated address), so every load of the hot loop is a local LDS;
+//   * one cluster barrier (barrier.cluster arrive.release / wait.acquire) per colour; the partial
+//     sums of |psi| ride on the second one: every warp pushes its partial to a slot in EVERY CTA of
+//     the cluster, after the barrier every warp adds the slots in a fixed order, so all threads of
+//     the cluster hold the same mean|psi| and run the reference's loop control (numbas.py:401-414)
+//     redundantly -- no extra synchronisation for the stop test;
+//   * the tile is laid out with one pad slot per run (row pitch of a run: K + 1 doubles, odd), which
+//     makes the strided accesses of a half-warp fall into distinct banks.
+// Operands are the padded / derived copies of the fused plan (xinv_march2d.cuh: Fd with the skip
+// marker, row values with the factor), so everything the marching engine accepts in its RC form
+// -- invert_Poisson, invert_GillMatsuno, invert_Stommel and their device front ends -- runs here
+// when the slice fits; arithmetic per cell: xm_eval / xm_eval_gen operation for operation
+// (numbas.py:351-369 with B == 0; :1132-1153), compiled with -fmad=false: the iterates are
+// bit-identical to the marching engine's, the colour engine's and the oracle's.
+// A batch runs one slice per cluster at a time (persistent clusters), each stopping on its own test.
+#pragma once
+#include <cooperative_groups.h>
+#include "xinv_march2d.cuh"
+
+namespace cg = cooperative_groups;
+
+struct XcArgs {
+    double *Sbuf[2];          // padded psi buffers of the fused plan [batch][ny][pitch]
+    const double *Fd;         // [cbFd ? batch : 1][ny][pitch]
+    const double *rows;       // [cbRow ? batch : 1][NV][rpitch]
+    i64 pitch, slice, rpitch;
+    int ny, nx, batch;
+    int bcy, bcx;
+    int cbFd, cbRow;
+    double ratioSqr, undef;
+    double ratio, delx, delxSqr;      // general form only
+    XdSliceState *st;
+    int *nactive;
+    double tol;
+    i64 mxLoop;
+    int zero_exit;
+    int nsweeps;              // sweep budget of this launch
+    int R;                    // CTAs per cluster
+    int WPR, RPR;             // warps per row, runs per row
+    int RPmax;                // rows of the tile besides the two halo rows (= max rows per CTA)
+    int TP;                   // tile pitch (doubles)
+    int NW;                   // warps per CTA
+};
+
+template <int KIND> struct XcRow;
+template <> struct XcRow<0> { double Ac, An, C, fac; };
+template <> struct XcRow<1> { double A, C, D, E, F, fac; };
+
+// one colour of a thread's run: cells m = PAR, PAR + 2, ... (< K)
+template <int KIND, int K, int PAR>
+__device__ __forceinline__ void xc_half(double (&psi)[K], const double (&fd)[K], const XcRow<KIND> &cr, const XcArgs &a,
+                                        double *Tc, const double *Tn, const double *Ts, int col0, int westIdx, int eastIdx,
+                                        bool act, bool ghostE, bool ghostW, int ghostEidx, double *pushN, double *pushS)
+{
+    constexpr int NC = (K - PAR + 1) / 2;
+    constexpr bool LASTIN = ((K - 1 - PAR) % 2) == 0;          // is cell K-1 of this colour?
+    double sn[NC], ss[NC];
+    #pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        sn[c] = Tn[col0 + PAR + 2 * c];
+        ss[c] = Ts[col0 + PAR + 2 * c];
+    }
+    double sw = 0.0, se = 0.0;
+    if (PAR == 0) sw = Tc[westIdx];
+    if (LASTIN) se = Tc[eastIdx];
+    #pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int m = PAR + 2 * c;
+        const double So = psi[m];
+        const double Sw = (m == 0) ? sw : psi[m > 0 ? m - 1 : 0];
+        const double Se = (m == K - 1) ? se : psi[m < K - 1 ? m + 1 : K - 1];
+        const double Snn = sn[c], Sss = ss[c];
+        double temp;
+        if constexpr (KIND == 0) {
+            const XcRow<0> &r = cr;
+            const double t1 = (r.An * (Snn - So) - r.Ac * (So - Sss)) * a.ratioSqr;
+            const double t4 = (r.C * (Se - So) - r.C * (So - Sw));
+            temp = (t1 + t4) - fd[m];
+            temp = temp * r.fac;
+        } else {
+            const XcRow<1> &g = cr;
+            temp = g.A * ((Snn - So) - (So - Sss)) * a.ratioSqr;
+            temp = temp + g.C * ((Se - So) - (So - Sw));
+            temp = temp + (g.D * (Snn - Sss) * a.ratio + g.E * (Se - Sw)) * a.delx / 2.0;
+            temp = temp + (g.F * So - fd[m]) * a.delxSqr;
+            temp = temp * g.fac;
+        }
+        const bool upd = __double2hiint(fd[m]) != XM_SKIP_HI;
+        const double nv = upd ? So + temp : So;
+        psi[m] = nv;
+        if (act) {
+            Tc[col0 + m] = nv;
+            if (m == 0 && ghostE) Tc[ghostEidx] = nv;          // column 0 -> the east ghost (periodic-x)
+            if (m == K - 1 && ghostW) Tc[0] = nv;              // column nx-1 -> the west ghost
+            if (pushN) pushN[col0 + m] = nv;                   // into the neighbouring CTAs' halo rows (DSMEM)
+            if (pushS) pushS[col0 + m] = nv;
+        }
+    }
+}
+
+template <int KIND, int K>
+__global__ void __launch_bounds__((K <= 4 ? 768 : K <= 6 ? 640 : K <= 8 ? 512 : K <= 12 ? 384 : 320), 1)
+xc_cluster_kernel(const XcArgs a)
+{
+    extern __shared__ __align__(16) unsigned char xc_smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int R = a.R;
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / R, ncl = gridDim.x / R;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ny = a.ny, nx = a.nx, TP = a.TP, NW = a.NW;
+    double *T = reinterpret_cast<double *>(xc_smem);                       // [(RPmax + 2)][TP]
+    double *slotS = T + (size_t)(a.RPmax + 2) * TP;                        // [R * NW]
+    int *slotN = reinterpret_cast<int *>(slotS + R * NW);                  // [R * NW]
+
+    const int j0 = (int)(((i64)rank * ny) / R), j1 = (int)(((i64)(rank + 1) * ny) / R);
+    const int nrows = j1 - j0;
+    const int jl = warp / a.WPR;
+    const int q = (warp - jl * a.WPR) * 32 + lane;
+    const bool act = (jl < nrows) && (q < a.RPR);
+    const int j = j0 + (jl < nrows ? jl : 0);
+    const int i0 = q * K;
+    int nvalid = nx - i0;
+    if (nvalid > K) nvalid = K;
+    if (!act || nvalid < 0) nvalid = 0;
+    const bool periodic = (a.bcx == XD_BC_PERIODIC);
+    const int col0 = 1 + q * (K + 1);
+    const int westIdx = (q > 0) ? col0 - 2 : 0;
+    const bool lastrun = act && (i0 + nvalid == nx);
+    const int ghostEidx = 1 + (a.RPR - 1) * (K + 1) + (nx - (a.RPR - 1) * K);   // the slot east of column nx-1
+    const int eastIdx = lastrun ? ghostEidx : col0 + K + 1;
+    const bool ghostE = periodic && act && (q == 0);
+    const bool ghostW = periodic && lastrun;
+    double *Tc = T + (size_t)(jl + 1) * TP;
+    const double *Tn = Tc + TP, *Ts = Tc - TP;
+    // halo rows of the neighbouring CTAs that mirror this thread's row
+    double *pushN = nullptr, *pushS = nullptr;
+    if (act && jl == nrows - 1 && rank + 1 < R) pushN = cluster.map_shared_rank(T, rank + 1);                  // their row j0' - 1
+    if (act && jl == 0 && rank > 0) {
+        const int pj0 = (int)(((i64)(rank - 1) * ny) / R);
+        pushS = cluster.map_shared_rank(T, rank - 1) + (size_t)(j0 - pj0 + 1) * TP;                            // their row j1'
+    }
+    const double undef = a.undef;
+    const int par0 = j & 1;                                       // colour 0 cells of this row: m = par0, par0 + 2, ...
+    const bool ext_lo = act && a.bcy == XD_BC_EXTEND && j == 0;
+    const bool ext_hi = act && a.bcy == XD_BC_EXTEND && j == ny - 1;
+    const bool ext_cta = a.bcy == XD_BC_EXTEND && (rank == 0 || rank == R - 1);
+
+    for (int b = cid; b < a.batch; b += ncl) {
+        XdSliceState st_ = a.st[b];
+        if (!st_.active) continue;                                // the same for every thread of the cluster
+        // ---- operands of this thread: psi, Fd of its run; the row values ----
+        double psi[K], fd[K];
+        {
+            const double *src = a.Sbuf[st_.cur] + (i64)b * a.slice + (i64)j * a.pitch + XM_PADL + i0;
+            const double *sf = a.Fd + (i64)(a.cbFd ? b : 0) * a.slice + (i64)j * a.pitch + XM_PADL + i0;
+            #pragma unroll
+            for (int m = 0; m < K; ++m) {
+                psi[m] = (m < nvalid) ? src[m] : undef;
+                fd[m] = (m < nvalid) ? sf[m] : xm_skip_value();
+            }
+        }
+        XcRow<KIND> cr;
+        {
+            const double *rv = a.rows + (i64)(a.cbRow ? b : 0) * (KIND == 0 ? 3 : 6) * a.rpitch;
+            if constexpr (KIND == 0) {
+                XcRow<0> &r = cr;
+                r.Ac = rv[j]; r.An = rv[j + 1 < ny ? j + 1 : j]; r.C = rv[a.rpitch + j]; r.fac = rv[2 * a.rpitch + j];
+            } else {
+                XcRow<1> &g = cr;
+                g.A = rv[j]; g.C = rv[a.rpitch + j]; g.D = rv[2 * a.rpitch + j]; g.E = rv[3 * a.rpitch + j];
+                g.F = rv[4 * a.rpitch + j]; g.fac = rv[5 * a.rpitch + j];
+            }
+        }
+        // ---- fill the tile: own rows (with the periodic ghosts), halo rows straight from HBM ----
+        if (act) {
+            #pragma unroll
+            for (int m = 0; m < K; ++m) Tc[col0 + m] = psi[m];
+            if (ghostE) Tc[ghostEidx] = psi[0];
+            if (ghostW) Tc[0] = psi[K - 1];
+            if (jl == nrows - 1 && j + 1 < ny) {
+                const double *src = a.Sbuf[st_.cur] + (i64)b * a.slice + (i64)(j + 1) * a.pitch + XM_PADL + i0;
+                #pragma unroll
+                for (int m = 0; m < K; ++m) if (m < nvalid) Tc[TP + col0 + m] = src[m];
+            }
+            if (jl == 0 && j > 0) {
+                const double *src = a.Sbuf[st_.cur] + (i64)b * a.slice + (i64)(j - 1) * a.pitch + XM_PADL + i0;
+                #pragma unroll
+                for (int m = 0; m < K; ++m) if (m < nvalid) Tc[-TP + col0 + m] = src[m];
+            }
+        }
+        cluster.sync();
+
+        for (int sweep = 0; sweep < a.nsweeps; ++sweep) {
+            // ---- y-"extend" rows (numbas.py:284-310): row 0 := row 1, row ny-1 := row ny-2 where != undef ----
+            if (ext_cta) {
+                if (ext_lo || ext_hi) {
+                    const double *Tr = ext_lo ? Tn : Ts;
+                    double sv[K + 2];
+                    sv[0] = Tr[westIdx];
+                    #pragma unroll
+                    for (int m = 0; m < K; ++m) sv[m + 1] = Tr[col0 + m];
+                    sv[K + 1] = Tr[eastIdx];
+                    #pragma unroll
+                    for (int m = 0; m < K; ++m) {
+                        double s = sv[m + 1];
+                        if (!periodic) {
+                            if (i0 + m == 0) s = sv[m + 2];                 // S[0,0] = S[1,1]
+                            if (i0 + m == nx - 1) s = sv[m];                // S[0,nx-1] = S[1,nx-2]
+                        }
+                        if (m < nvalid && s != undef) psi[m] = s;
+                        Tc[col0 + m] = psi[m];
+                    }
+                }
+                __syncthreads();                                   // row 1 / ny-2 read the new rows (same CTA)
+            }
+            // ---- colour 0, colour 1: one cluster barrier each ----
+            if (par0 == 0) xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, pushN, pushS);
+            else           xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, pushN, pushS);
+            cluster.sync();
+            if (par0 == 0) xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, pushN, pushS);
+            else           xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, pushN, pushS);
+            // ---- sum|psi|, count over psi != undef (numbas.py:1710-1728): thread -> warp -> a slot in every CTA ----
+            double s = 0.0;
+            int n = 0;
+            #pragma unroll
+            for (int m = 0; m < K; ++m) {
+                const double v = psi[m];
+                if (v != undef) { s += fabs(v); n += 1; }          // slots beyond the run hold undef
+            }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                n += __shfl_xor_sync(0xffffffffu, n, o);
+            }
+            if (lane < R) {
+                double *rs = cluster.map_shared_rank(slotS, lane);
+                int *rn = cluster.map_shared_rank(slotN, lane);
+                rs[rank * NW + warp] = s;
+                rn[rank * NW + warp] = n;
+            }
+            cluster.sync();
+            double ts = 0.0;
+            i64 tn = 0;
+            for (int k = lane; k < R * NW; k += 32) { ts += slotS[k]; tn += slotN[k]; }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ts += __shfl_xor_sync(0xffffffffu, ts, o);
+                tn += __shfl_xor_sync(0xffffffffu, tn, o);
+            }
+            xd_decide(st_, ts, tn, a.tol, a.mxLoop, a.zero_exit);  // every thread of the cluster, identically
+            if (!st_.active) break;
+        }
+        // ---- psi back to the plan's buffer, state back ----
+        if (act) {
+            double *dst = a.Sbuf[st_.cur] + (i64)b * a.slice + (i64)j * a.pitch + XM_PADL + i0;
+            #pragma unroll
+            for (int m = 0; m < K; ++m) if (m < nvalid) dst[m] = psi[m];
+        }
+        if (rank == 0 && tid == 0) {
+            a.st[b] = st_;
+            if (!st_.active) atomicSub(a.nactive, 1);
+        }
+        cluster.sync();                                            // nobody writes into a tile that is being refilled
+    }
+    cluster.sync();                                                // no CTA leaves while its shared memory may be addressed
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+struct ClusterPlan {
+    bool built = false;
+    XcArgs args{};
+    int kind = 0, K = 0, R = 1;
+    int threads = 0, grid = 0;
+    size_t smem = 0;
+};
+
+static inline void cluster_plan_release(ClusterPlan &p) { p = ClusterPlan(); }
+
+static const int XC_KS[] = {4, 6, 8, 12, 16};
+#define XC_NK ((int)(sizeof(XC_KS) / sizeof(XC_KS[0])))
+
+#define XC_DISPATCH(kind, K, CALL)                       \
+    if ((kind) == 0) switch (K) {                        \
+    case 4: CALL(0, 4); break;                           \
+    case 6: CALL(0, 6); break;                           \
+    case 8: CALL(0, 8); break;                           \
+    case 12: CALL(0, 12); break;                         \
+    default: CALL(0, 16); break;                         \
+    } else switch (K) {                                  \
+    case 4: CALL(1, 4); break;                           \
+    case 6: CALL(1, 6); break;                           \
+    case 8: CALL(1, 8); break;                           \
+    case 12: CALL(1, 12); break;                         \
+    default: CALL(1, 16); break;                         \
+    }
+
+template <int KIND, int K>
+static cudaError_t xc_attr(size_t smem, int R, int *max_threads)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, xc_cluster_kernel<KIND, K>);
+    if (e != cudaSuccess) return e;
+    *max_threads = fa.maxThreadsPerBlock;
+    if ((e = cudaFuncSetAttribute(xc_cluster_kernel<KIND, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+        return e;
+    if (R > 8) e = cudaFuncSetAttribute(xc_cluster_kernel<KIND, K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return e;
+}
+
+template <int KIND, int K>
+static cudaError_t xc_launch(const ClusterPlan &p, cudaStream_t stream, int *max_clusters)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(max_clusters ? p.R : p.grid));
+    cfg.blockDim = dim3((unsigned)p.threads);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.R;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters) return cudaOccupancyMaxActiveClusters(max_clusters, xc_cluster_kernel<KIND, K>, &cfg);
+    return cudaLaunchKernelEx(&cfg, xc_cluster_kernel<KIND, K>, p.args);
+}
+
+// Pick (R, K) for a slice of ny x nx and a batch; returns false when no shape fits.
+// Model of one half sweep (cycles): a cluster barrier, a fixed part, and the updates of one colour --
+// K/2 cells per thread, ~40 issue cycles of FP64 work per cell and warp, the warps of an SM sub-partition one
+// after the other.  Over the batch: clusters run side by side, floor(SMs / R) at a time.
+static inline bool xc_choose(int ny, int nx, bool periodic, i64 batch, int sm_count, const int *max_threads /*[XC_NK]*/,
+                             int *R_out, int *K_out)
+{
+    const char *eR = getenv("XINV_CLUSTER_R"), *eK = getenv("XINV_CLUSTER_K");
+    double best = 1e300;
+    bool found = false;
+    for (int R = 16; R >= 1; R >>= 1) {
+        if (eR && atoi(eR) != R) continue;
+        if (ny / R < 2 && R > 1) continue;                  // every CTA holds at least two rows (y-extend stays inside a CTA)
+        const int RPmax = (ny + R - 1) / R;
+        for (int k = 0; k < XC_NK; ++k) {
+            const int K = XC_KS[k];
+            if (eK && atoi(eK) != K) continue;
+            if (periodic && nx % K != 0) continue;          // the last run ends at column nx-1 (its east neighbour is the ghost)
+            const int RPR = (nx + K - 1) / K, WPR = (RPR + 31) / 32;
+            const int warps = RPmax * WPR;
+            if (warps * 32 > max_threads[k] || warps > 32) continue;
+            const size_t smem = ((size_t)(RPmax + 2) * (2 + (size_t)WPR * 32 * (K + 1)) + (size_t)R * warps * 2) * 8 + 64;
+            if (smem > 200 * 1024) continue;
+            const double half = (R > 1 ? 400.0 : 60.0) + 150.0 + (K / 2) * 40.0 * ((warps + 3) / 4);
+            const i64 side = sm_count / R;
+            const double waves = (double)((batch + side - 1) / side);
+            const double cost = half * waves;
+            if (cost < best) { best = cost; *R_out = R; *K_out = K; found = true; }
+        }
+    }
+    return found;
+}
+
+// Build on top of a fused plan with row coefficients (p.rc): same operands, another way through them.
+static inline int cluster_plan_build(ClusterPlan &cp, const FusedPlan &fp, int sm_count, const XdGeom &g, const XdCoef &q,
+                                     i64 batch, std::string &why)
+{
+    cluster_plan_release(cp);
+    if (!fp.built || !fp.rc) { why = "cluster engine needs coefficients constant along x"; return -1; }
+    const XmArgs &fa = fp.args;
+    const bool periodic = (g.bcx == XD_BC_PERIODIC);
+    int max_threads[XC_NK];
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < XC_NK; ++k) {
+        int mt = 0;
+#define XC_ATTR(KD, K_) e = xc_attr<KD, K_>(200 * 1024, 16, &mt)
+        XC_DISPATCH(fp.kind, XC_KS[k], XC_ATTR);
+#undef XC_ATTR
+        if (e != cudaSuccess) { why = std::string("cluster kernel attributes: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return -1; }
+        max_threads[k] = mt;
+    }
+    int R = 1, K = 4;
+    if (!xc_choose((int)g.ny, (int)g.nx, periodic, batch, sm_count, max_threads, &R, &K)) {
+        why = "slice does not fit a thread-block cluster";
+        return -1;
+    }
+    XcArgs &a = cp.args;
+    a.Sbuf[0] = fa.Sbuf[0]; a.Sbuf[1] = fa.Sbuf[1];
+    a.Fd = (const double *)fp.bufFd; a.rows = (const double *)fp.bufRow;
+    a.pitch = fa.pitch; a.slice = fa.slice; a.rpitch = (g.ny + 3) / 4 * 4;
+    a.ny = (int)g.ny; a.nx = (int)g.nx; a.batch = (int)batch;
+    a.bcy = g.bcy; a.bcx = g.bcx;
+    a.cbFd = fa.cbFd; a.cbRow = fa.cbRow;
+    a.ratioSqr = fa.ratioSqr; a.undef = q.undef; a.ratio = fa.ratio; a.delx = fa.delx; a.delxSqr = fa.delxSqr;
+    a.R = R;
+    a.RPR = (int)((g.nx + K - 1) / K);
+    a.WPR = (a.RPR + 31) / 32;
+    a.RPmax = (int)((g.ny + R - 1) / R);
+    a.TP = 2 + a.WPR * 32 * (K + 1);
+    a.NW = a.RPmax * a.WPR;
+    cp.kind = fp.kind; cp.K = K; cp.R = R;
+    cp.threads = a.NW * 32;
+    cp.smem = ((size_t)(a.RPmax + 2) * a.TP + (size_t)R * a.NW * 2) * sizeof(double) + 64;
+    int maxcl = 0;
+#define XC_OCC(KD, K_) e = xc_launch<KD, K_>(cp, 0, &maxcl)
+    XC_DISPATCH(cp.kind, cp.K, XC_OCC);
+#undef XC_OCC
+    if (e != cudaSuccess || maxcl < 1) {
+        why = std::string("no cluster of ") + std::to_string(R) + " CTAs can be resident: " + cudaGetErrorString(e);
+        (void)cudaGetLastError();
+        cluster_plan_release(cp);
+        return -1;
+    }
+    const i64 ncl = batch < maxcl ? batch : maxcl;
+    cp.grid = (int)(ncl * R);
+    cp.built = true;
+    return 0;
+}
+
+static inline int cluster_sweep(ClusterPlan &p, cudaStream_t stream, XdSliceState *st, int *nactive, double tol, i64 mxLoop,
+                                int zero_exit, int nsweeps, int64_t *launches)
+{
+    XcArgs &a = p.args;
+    a.st = st; a.nactive = nactive; a.tol = tol; a.mxLoop = mxLoop; a.zero_exit = zero_exit; a.nsweeps = nsweeps;
+    cudaError_t e = cudaSuccess;
+#define XC_GO(KD, K_) e = xc_launch<KD, K_>(p, stream, nullptr)
+    XC_DISPATCH(p.kind, p.K, XC_GO);
+#undef XC_GO
+    if (e != cudaSuccess) return -1;
+    *launches += 1;
+    return 0;
+}

@@ -1,0 +1,252 @@
+// xinv_resident.cuh -- XINV_ENGINE_RESIDENT: the whole solve of a SMALL 2-D slice in one CTA.
+//
+// Slices whose operands fit into the shared memory of one SM (a few thousand cells: the z-lat
+// sections of invert_Eliassen, tests/test_Eliassen.py:15-232 of the reference -- 37 x 73 --, small
+// Gill-Matsuno / Stommel / Poisson domains) are bound by launch latency on every other engine:
+// one sweep is 3-6 kernel launches of ~2 us each for a few hundred nanoseconds of work.  Here a
+// CTA stages psi and every coefficient array of its slice into shared memory once (bulk TMA
+// copies, cp.async.bulk, completion on an mbarrier), then iterates without leaving the SM:
+//   per sweep:  [y-extend rows] -> colour 0 .. ncol-1 in place (__syncthreads in between)
+//               -> mean|psi| by a deterministic block reduction -> numbas.py:401-414 by thread 0
+// until the slice stops or the launch's sweep budget is used up, and writes psi back.
+// All stencils of the 2-D forms are handled (5-point, 9-point with B != 0: four colours, the
+// general form; wrap-fix colours for periodic-x with odd nx): the per-cell updates are the very
+// functions of the colour engine (xd_update_std2d / xd_update_gen2d, reference expressions
+// numbas.py:344-369 / :1126-1153) applied to shared-memory pointers, the colouring is
+// xd_colour() -- so the iterates are bit-identical to the colour engine's and the oracle's.
+// A batch runs one slice per CTA (persistent over the batch), each stopping on its own test.
+#pragma once
+#include "xinv_colour_engine.cuh"
+#include "xinv_march2d.cuh"          // mbarrier / bulk-copy helpers
+
+#define XR_THREADS 512
+
+__device__ __forceinline__ void xr_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(xf_smem_u32(dst)), "l"(src), "r"(bytes), "r"(xf_smem_u32(bar)) : "memory");
+}
+
+struct XrArgs {
+    double *S;                // [batch][N]
+    XdCoef q;
+    XdGeom g;
+    int narr;                 // arrays staged per slice besides psi (coefficients + forcing, NULL B left out)
+    int slot[8];              // slot[m] = index of coefficient m in shared memory (1-based after psi), -1 = absent
+    int batch;
+    XdSliceState *st;
+    int *nactive;
+    double tol;
+    i64 mxLoop;
+    int zero_exit;
+    int nsweeps;              // sweep budget of this launch
+};
+
+template <int KIND, bool HASB>
+__global__ void __launch_bounds__(XR_THREADS, 1)
+xr_resident_kernel(const XrArgs a)
+{
+    extern __shared__ __align__(128) unsigned char xr_smem[];
+    const XdGeom &g = a.g;
+    const i64 N = g.N;
+    const i64 Np = (N + 1) & ~(i64)1;            // arrays start 16-byte aligned
+    double *sm = reinterpret_cast<double *>(xr_smem);
+    double *sS = sm;
+    double *red_sum = sm + (size_t)(a.narr + 1) * Np;          // [32]
+    i64 *red_cnt = reinterpret_cast<i64 *>(red_sum + 32);       // [32]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(red_cnt + 32);
+    int *flag = reinterpret_cast<int *>(bar + 1);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    unsigned phase = 0;
+    if (tid == 0) { xf_mbar_init(bar, 1); xf_fence_barrier_init(); }
+    __syncthreads();
+
+    const i64 nx = g.nx, ny = g.ny;
+    const int base = (g.scheme == 4) ? 4 : 2;
+    const i64 half = (nx + 1) / 2;
+    const i64 rows = (ny >= 3) ? ny - 2 : 0;
+    const double undef = a.q.undef;
+
+    for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+        if (tid == 0) flag[0] = a.st[b].active;
+        __syncthreads();
+        const int active0 = flag[0];
+        __syncthreads();
+        if (!active0) continue;
+
+        // ---- stage psi and the coefficient arrays of slice b (bulk TMA where 16-byte alignment allows) ----
+        const double *src[9];
+        double *dst[9];
+        src[0] = a.S + (i64)b * N; dst[0] = sS;
+        int na = 1;
+        for (int m = 0; m < 8; ++m) {
+            if (a.slot[m] < 0) continue;
+            src[na] = a.q.c[m] + (i64)b * a.q.cs[m];
+            dst[na] = sm + (size_t)a.slot[m] * Np;
+            ++na;
+        }
+        const uint32_t nb16 = (uint32_t)((N / 2) * 16);          // bytes that can go as one bulk copy per array
+        bool bulk = nb16 >= 16;
+        for (int m = 0; m < na; ++m) bulk = bulk && ((reinterpret_cast<uintptr_t>(src[m]) & 15) == 0);
+        if (bulk) {
+            if (tid == 0) {
+                xf_fence_proxy_async();          // the previous slice was read / written through the generic proxy
+                xf_mbar_expect_tx(bar, nb16 * (uint32_t)na);
+                for (int m = 0; m < na; ++m) xr_bulk_g2s(dst[m], src[m], nb16, bar);
+            }
+            if ((N & 1) && tid < na) dst[tid][N - 1] = src[tid][N - 1];     // the odd tail
+            xf_mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int m = 0; m < na; ++m)
+                for (i64 p = tid; p < N; p += nth) dst[m][p] = src[m][p];
+        }
+        __syncthreads();
+        const double *cA = (a.slot[0] >= 0) ? sm + (size_t)a.slot[0] * Np : nullptr;
+        const double *cB = (HASB && a.slot[1] >= 0) ? sm + (size_t)a.slot[1] * Np : nullptr;
+        const double *c2 = (a.slot[2] >= 0) ? sm + (size_t)a.slot[2] * Np : nullptr;
+        const double *c3 = (a.slot[3] >= 0) ? sm + (size_t)a.slot[3] * Np : nullptr;
+        const double *c4 = (KIND == XD_GEN2D) ? sm + (size_t)a.slot[4] * Np : nullptr;
+        const double *c5 = (KIND == XD_GEN2D) ? sm + (size_t)a.slot[5] * Np : nullptr;
+        const double *c6 = (KIND == XD_GEN2D) ? sm + (size_t)a.slot[6] * Np : nullptr;
+
+        XdSliceState st_;
+        if (tid == 0) st_ = a.st[b];
+        for (int sweep = 0; sweep < a.nsweeps; ++sweep) {
+            // ---- y-"extend" rows (numbas.py:284-310), as xd_extend_kernel ----
+            if (g.bcy == XD_BC_EXTEND) {
+                for (i64 i = tid; i < nx; i += nth) {
+                    i64 s_ = i;
+                    if (g.bcx != XD_BC_PERIODIC) { if (i == 0) s_ = 1; else if (i == nx - 1) s_ = nx - 2; }
+                    const double v0 = sS[nx + s_], v1 = sS[(ny - 2) * nx + s_];
+                    if (v0 != undef) sS[i] = v0;
+                    if (v1 != undef) sS[(ny - 1) * nx + i] = v1;
+                }
+                __syncthreads();
+            }
+            // ---- the colours, in place ----
+            for (int colour = 0; colour < g.ncol; ++colour) {
+                const i64 cells = (colour >= base) ? rows : rows * half;
+                for (i64 idx = tid; idx < cells; idx += nth) {
+                    i64 j, i;
+                    if (colour >= base) {                      // wrap-fix colours: column nx-1 only
+                        j = 1 + idx; i = nx - 1;
+                    } else {
+                        const i64 r = idx / half, m = idx - r * half;
+                        j = 1 + r;
+                        if (g.scheme == 4) {
+                            if ((int)(j & 1) != (colour >> 1)) continue;
+                            i = 2 * m + (colour & 1);
+                        } else {
+                            i = 2 * m + ((j + colour) & 1);
+                        }
+                    }
+                    if (i < g.i0 || i >= g.i1) continue;
+                    if (xd_colour(g.scheme, g.wrapfix, nx, j, j, i) != colour) continue;
+                    const i64 ip = (i == nx - 1) ? 0 : i + 1;
+                    const i64 im = (i == 0) ? nx - 1 : i - 1;
+                    if (KIND == XD_STD2D)
+                        xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2], a.q.optArg, undef);
+                    else
+                        xd_update_gen2d<HASB>(sS, cA, cB, c2, c3, c4, c5, c6, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2],
+                                              a.q.p[3], a.q.p[4], a.q.optArg, undef);
+                }
+                __syncthreads();
+            }
+            // ---- mean|psi| over psi != undef (numbas.py:1710-1728), loop control by thread 0 ----
+            double sum = 0.0;
+            i64 cnt = 0;
+            for (i64 p = tid; p < N; p += nth) {
+                const double v = sS[p];
+                if (v != undef) { sum += fabs(v); cnt += 1; }
+            }
+            xd_block_reduce(sum, cnt, red_sum, red_cnt);
+            if (tid == 0) {
+                xd_decide(st_, sum, cnt, a.tol, a.mxLoop, a.zero_exit);
+                flag[0] = st_.active;
+            }
+            __syncthreads();
+            const int go_on = flag[0];
+            __syncthreads();
+            if (!go_on) break;
+        }
+        // ---- psi back to HBM, state back ----
+        double *out = a.S + (i64)b * N;
+        for (i64 p = tid; p < N; p += nth) out[p] = sS[p];
+        if (tid == 0) {
+            a.st[b] = st_;
+            if (!st_.active) atomicSub(a.nactive, 1);
+        }
+        xf_fence_proxy_async();              // this slice's generic-proxy accesses before the next slice's bulk copies
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+struct ResidentPlan {
+    bool built = false;
+    XrArgs args{};
+    size_t smem = 0;
+    int grid = 0;
+    int kind = 0;
+    bool hasB = false;
+};
+
+static inline void resident_plan_release(ResidentPlan &p) { p = ResidentPlan(); }
+
+template <int KIND, bool HASB>
+static cudaError_t xr_prepare(size_t smem, int *blocks_per_sm)
+{
+    cudaError_t e = cudaFuncSetAttribute(xr_resident_kernel<KIND, HASB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, xr_resident_kernel<KIND, HASB>, XR_THREADS, smem);
+}
+
+// Does a slice with all its operands fit into the shared memory of one SM?
+static inline int resident_plan_build(ResidentPlan &p, int sm_count, int kind, bool hasB, const XdGeom &g, const XdCoef &q,
+                                      i64 batch, double *dS, std::string &why)
+{
+    resident_plan_release(p);
+    if (kind != XD_STD2D && kind != XD_GEN2D) { why = "2-D problems only"; return -1; }
+    if (g.ny < 3 || g.nx < 3) { why = "grid too small"; return -1; }
+    const int ncoef = (kind == XD_STD2D) ? 4 : 7;
+    XrArgs &a = p.args;
+    a.narr = 0;
+    for (int m = 0; m < 8; ++m) a.slot[m] = -1;
+    for (int m = 0; m < ncoef; ++m) {
+        if (!q.c[m]) continue;                   // B == NULL
+        a.slot[m] = ++a.narr;
+    }
+    const i64 Np = (g.N + 1) & ~(i64)1;
+    p.smem = (size_t)(a.narr + 1) * Np * sizeof(double) + 32 * 16 + 64;
+    if (p.smem > 220 * 1024) { why = "slice does not fit into shared memory"; return -1; }
+    int bps = 0;
+    cudaError_t e;
+    if (kind == XD_STD2D) e = hasB ? xr_prepare<XD_STD2D, true>(p.smem, &bps) : xr_prepare<XD_STD2D, false>(p.smem, &bps);
+    else                  e = hasB ? xr_prepare<XD_GEN2D, true>(p.smem, &bps) : xr_prepare<XD_GEN2D, false>(p.smem, &bps);
+    if (e != cudaSuccess || bps < 1) { why = std::string("resident kernel does not fit: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return -1; }
+    a.S = dS; a.q = q; a.g = g; a.batch = (int)batch;
+    const i64 slots = (i64)sm_count * bps;
+    p.grid = (int)(batch < slots ? batch : slots);
+    p.kind = kind; p.hasB = hasB;
+    p.built = true;
+    return 0;
+}
+
+static inline int resident_sweep(ResidentPlan &p, cudaStream_t stream, XdSliceState *st, int *nactive, double tol, i64 mxLoop,
+                                 int zero_exit, int nsweeps, int64_t *launches)
+{
+    XrArgs &a = p.args;
+    a.st = st; a.nactive = nactive; a.tol = tol; a.mxLoop = mxLoop; a.zero_exit = zero_exit; a.nsweeps = nsweeps;
+    if (p.kind == XD_STD2D) {
+        if (p.hasB) xr_resident_kernel<XD_STD2D, true><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
+        else        xr_resident_kernel<XD_STD2D, false><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
+    } else {
+        if (p.hasB) xr_resident_kernel<XD_GEN2D, true><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
+        else        xr_resident_kernel<XD_GEN2D, false><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
+    }
+    *launches += 1;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
