@@ -15,11 +15,14 @@
 //     and below) for the north/south neighbours; a value in the first / last row of a CTA is also
 //     pushed straight into the halo row of the neighbouring CTA's tile through distributed shared
 //     memory (st to a mapa-translated address), so every load of the hot loop is a local LDS;
-//   * one cluster barrier (barrier.cluster arrive.release / wait.acquire) per colour; the partial
-//     sums of |psi| ride on the second one: every warp pushes its partial to a slot in EVERY CTA of
-//     the cluster, after the barrier every warp adds the slots in a fixed order, so all threads of
-//     the cluster hold the same mean|psi| and run the reference's loop control (numbas.py:401-414)
-//     redundantly -- no extra synchronisation for the stop test;
+//   * no cluster barrier in the loop: the pushes are st.async stores that complete a transaction count
+//     on an mbarrier in the RECEIVER's shared memory, so a CTA only waits -- in the warps of its first
+//     and last row -- for the halo values of its two neighbours; inside the CTA one __syncthreads per
+//     colour orders the tile;
+//   * the partial sums of |psi| travel the same way: every warp pushes its (sum, count) to a slot in
+//     EVERY CTA of the cluster, every warp adds the slots in a fixed order once they have arrived, so
+//     all threads of the cluster hold the same mean|psi| and run the reference's loop control
+//     (numbas.py:401-414) redundantly -- no further synchronisation for the stop test;
 //   * the tile is laid out with one pad slot per run (row pitch of a run: K + 1 doubles, odd), which
 //     makes the strided accesses of a half-warp fall into distinct banks.
 // Operands are the padded / derived copies of the fused plan (xinv_march2d.cuh: Fd with the skip
@@ -62,11 +65,35 @@ template <int KIND> struct XcRow;
 template <> struct XcRow<0> { double Ac, An, C, fac; };
 template <> struct XcRow<1> { double A, C, D, E, F, fac; };
 
+// ---- DSMEM plumbing --------------------------------------------------------------------------------
+// A value for another CTA of the cluster travels as st.async (SASS: STAS): a store into the peer's shared
+// memory that completes a transaction count on an mbarrier IN THE PEER'S shared memory.  The consumer waits
+// on its own mbarrier, so data and "it has arrived" come as one message and no fence is needed -- the
+// release/acquire pair of barrier.cluster costs a MEMBAR.ALL.GPU per barrier with this toolchain
+// (cuobjdump), 3.5 us per sweep on 360 x 180 against 1.x us this way.
+__device__ __forceinline__ uint32_t xc_mapa(uint32_t saddr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void xc_st_async(uint32_t raddr, double v, uint32_t rbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];"
+                 ::"r"(raddr), "d"(v), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void xc_st_async2(uint32_t raddr, double v, double w, uint32_t rbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+                 ::"r"(raddr), "d"(v), "d"(w), "r"(rbar) : "memory");
+}
+
 // one colour of a thread's run: cells m = PAR, PAR + 2, ... (< K)
 template <int KIND, int K, int PAR>
 __device__ __forceinline__ void xc_half(double (&psi)[K], const double (&fd)[K], const XcRow<KIND> &cr, const XcArgs &a,
                                         double *Tc, const double *Tn, const double *Ts, int col0, int westIdx, int eastIdx,
-                                        bool act, bool ghostE, bool ghostW, int ghostEidx, double *pushN, double *pushS)
+                                        bool act, bool ghostE, bool ghostW, int ghostEidx,
+                                        uint32_t rN, uint32_t rbN, uint32_t rS, uint32_t rbS)
 {
     constexpr int NC = (K - PAR + 1) / 2;
     constexpr bool LASTIN = ((K - 1 - PAR) % 2) == 0;          // is cell K-1 of this colour?
@@ -102,38 +129,58 @@ __device__ __forceinline__ void xc_half(double (&psi)[K], const double (&fd)[K],
             temp = temp * g.fac;
         }
         const bool upd = __double2hiint(fd[m]) != XM_SKIP_HI;
-        const double nv = upd ? So + temp : So;
-        psi[m] = nv;
-        if (act) {
-            Tc[col0 + m] = nv;
-            if (m == 0 && ghostE) Tc[ghostEidx] = nv;          // column 0 -> the east ghost (periodic-x)
-            if (m == K - 1 && ghostW) Tc[0] = nv;              // column nx-1 -> the west ghost
-            if (pushN) pushN[col0 + m] = nv;                   // into the neighbouring CTAs' halo rows (DSMEM)
-            if (pushS) pushS[col0 + m] = nv;
+        psi[m] = upd ? So + temp : So;
+    }
+    if (act) {
+        #pragma unroll
+        for (int c = 0; c < NC; ++c) Tc[col0 + PAR + 2 * c] = psi[PAR + 2 * c];
+        if (PAR == 0 && ghostE) Tc[ghostEidx] = psi[0];            // column 0 -> the east ghost (periodic-x)
+        if (LASTIN && ghostW) Tc[0] = psi[K - 1];                  // column nx-1 -> the west ghost
+        if (rN) {                                                  // into the neighbouring CTAs' halo rows (DSMEM)
+            #pragma unroll
+            for (int c = 0; c < NC; ++c) xc_st_async(rN + 8u * (uint32_t)(col0 + PAR + 2 * c), psi[PAR + 2 * c], rbN);
+        }
+        if (rS) {
+            #pragma unroll
+            for (int c = 0; c < NC; ++c) xc_st_async(rS + 8u * (uint32_t)(col0 + PAR + 2 * c), psi[PAR + 2 * c], rbS);
         }
     }
 }
 
+// The block has NW compute warps (a row segment each) and ONE CONTROL WARP (the last one): it owns no cells, posts the
+// transaction counts, and -- while the compute warps are busy with colour 0 of the next sweep -- waits for the norm
+// partials of the sweep just finished, adds them up and runs the reference's loop control; the compute warps pick the
+// verdict up at the CTA barrier that ends colour 0.
 template <int KIND, int K>
-__global__ void __launch_bounds__((K <= 4 ? 768 : K <= 6 ? 640 : K <= 8 ? 512 : K <= 12 ? 384 : 320), 1)
+__global__ void __launch_bounds__((K <= 6 ? 512 : K <= 8 ? 448 : K <= 12 ? 416 : 320), 1)
 xc_cluster_kernel(const XcArgs a)
 {
+    static_assert(K % 2 == 0, "runs hold whole red/black pairs");
     extern __shared__ __align__(16) unsigned char xc_smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int R = a.R;
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / R, ncl = gridDim.x / R;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nth = blockDim.x;
     const int ny = a.ny, nx = a.nx, TP = a.TP, NW = a.NW;
+    const bool ctrl = (warp == NW);
     double *T = reinterpret_cast<double *>(xc_smem);                       // [(RPmax + 2)][TP]
-    double *slotS = T + (size_t)(a.RPmax + 2) * TP;                        // [R * NW]
-    int *slotN = reinterpret_cast<int *>(slotS + R * NW);                  // [R * NW]
+    double2 *slot = reinterpret_cast<double2 *>(T + (size_t)(a.RPmax + 2) * TP);   // [2][R * NW]: (sum, count) per compute warp of the cluster
+    double *bkT = reinterpret_cast<double *>(slot + 2 * R * NW);           // [K / 2][threads]: the red cells before a speculative half sweep
+    uint64_t *hb = reinterpret_cast<uint64_t *>(bkT + (size_t)(K / 2) * nth);   // [2] halo values of colour 0 / 1 have arrived
+    uint64_t *nb = hb + 2;                                                 // [2] norm partials have arrived (by parity of the sweep)
+    int *verdict = reinterpret_cast<int *>(nb + 2);                        // [1] "the slice goes on", written by the control warp
+    if (tid == 0) {
+        xf_mbar_init(hb, 1); xf_mbar_init(hb + 1, 1); xf_mbar_init(nb, 1); xf_mbar_init(nb + 1, 1);
+        xf_fence_barrier_init();
+    }
+    cluster.sync();
 
     const int j0 = (int)(((i64)rank * ny) / R), j1 = (int)(((i64)(rank + 1) * ny) / R);
     const int nrows = j1 - j0;
     const int jl = warp / a.WPR;
     const int q = (warp - jl * a.WPR) * 32 + lane;
-    const bool act = (jl < nrows) && (q < a.RPR);
+    const bool act = !ctrl && (jl < nrows) && (q < a.RPR);
     const int j = j0 + (jl < nrows ? jl : 0);
     const int i0 = q * K;
     int nvalid = nx - i0;
@@ -147,28 +194,42 @@ xc_cluster_kernel(const XcArgs a)
     const int eastIdx = lastrun ? ghostEidx : col0 + K + 1;
     const bool ghostE = periodic && act && (q == 0);
     const bool ghostW = periodic && lastrun;
-    double *Tc = T + (size_t)(jl + 1) * TP;
+    double *Tc = T + (size_t)((ctrl ? 0 : jl) + 1) * TP;
     const double *Tn = Tc + TP, *Ts = Tc - TP;
-    // halo rows of the neighbouring CTAs that mirror this thread's row
-    double *pushN = nullptr, *pushS = nullptr;
-    if (act && jl == nrows - 1 && rank + 1 < R) pushN = cluster.map_shared_rank(T, rank + 1);                  // their row j0' - 1
-    if (act && jl == 0 && rank > 0) {
-        const int pj0 = (int)(((i64)(rank - 1) * ny) / R);
-        pushS = cluster.map_shared_rank(T, rank - 1) + (size_t)(j0 - pj0 + 1) * TP;                            // their row j1'
+    // halo rows of the neighbouring CTAs that mirror this thread's row, and the neighbours' halo barriers
+    const bool hasN = rank + 1 < R, hasS = rank > 0;
+    const bool edgeN = !ctrl && hasN && jl == nrows - 1, edgeS = !ctrl && hasS && jl == 0;      // warp-uniform
+    uint32_t rN = 0, rS = 0, rbN[2] = {0, 0}, rbS[2] = {0, 0};
+    if (edgeN) {
+        rN = xc_mapa(xf_smem_u32(T), rank + 1);                                  // their row j0' - 1
+        rbN[0] = xc_mapa(xf_smem_u32(hb), rank + 1); rbN[1] = xc_mapa(xf_smem_u32(hb + 1), rank + 1);
     }
+    if (edgeS) {
+        const int pj0 = (int)(((i64)(rank - 1) * ny) / R);
+        rS = xc_mapa(xf_smem_u32(T + (size_t)(j0 - pj0 + 1) * TP), rank - 1);    // their row j1'
+        rbS[0] = xc_mapa(xf_smem_u32(hb), rank - 1); rbS[1] = xc_mapa(xf_smem_u32(hb + 1), rank - 1);
+    }
+    const uint32_t halo_bytes = (uint32_t)((hasN ? 1 : 0) + (hasS ? 1 : 0)) * (uint32_t)a.RPR * (K / 2) * 8u;
+    const uint32_t norm_bytes = (uint32_t)(R * NW) * 16u;
     const double undef = a.undef;
     const int par0 = j & 1;                                       // colour 0 cells of this row: m = par0, par0 + 2, ...
+    const bool upd_row = act && j > 0 && j < ny - 1;              // rows 0 and ny-1 are never updated (warp-uniform)
     const bool ext_lo = act && a.bcy == XD_BC_EXTEND && j == 0;
     const bool ext_hi = act && a.bcy == XD_BC_EXTEND && j == ny - 1;
     const bool ext_cta = a.bcy == XD_BC_EXTEND && (rank == 0 || rank == R - 1);
+    const bool post = ctrl && lane == 0;                          // the thread that posts transaction counts
+    unsigned sp = 0;                                              // completed sweeps so far: which norm barrier, which parity
+    unsigned ph0 = 0, ph1 = 0;                                    // phases of the two halo barriers so far (a sweep that is undone has used hb[0] only)
 
     for (int b = cid; b < a.batch; b += ncl) {
-        XdSliceState st_ = a.st[b];
-        if (!st_.active) continue;                                // the same for every thread of the cluster
+        if (!a.st[b].active) continue;                            // the same for every thread of the cluster
+        const int cur = a.st[b].cur;
+        XdSliceState st_;                                         // lives in the control warp
+        if (ctrl) st_ = a.st[b];
         // ---- operands of this thread: psi, Fd of its run; the row values ----
         double psi[K], fd[K];
         {
-            const double *src = a.Sbuf[st_.cur] + (i64)b * a.slice + (i64)j * a.pitch + XM_PADL + i0;
+            const double *src = a.Sbuf[cur] + (i64)b * a.slice + (i64)j * a.pitch + XM_PADL + i0;
             const double *sf = a.Fd + (i64)(a.cbFd ? b : 0) * a.slice + (i64)j * a.pitch + XM_PADL + i0;
             #pragma unroll
             for (int m = 0; m < K; ++m) {
@@ -195,20 +256,26 @@ xc_cluster_kernel(const XcArgs a)
             if (ghostE) Tc[ghostEidx] = psi[0];
             if (ghostW) Tc[0] = psi[K - 1];
             if (jl == nrows - 1 && j + 1 < ny) {
-                const double *src = a.Sbuf[st_.cur] + (i64)b * a.slice + (i64)(j + 1) * a.pitch + XM_PADL + i0;
+                const double *src = a.Sbuf[cur] + (i64)b * a.slice + (i64)(j + 1) * a.pitch + XM_PADL + i0;
                 #pragma unroll
                 for (int m = 0; m < K; ++m) if (m < nvalid) Tc[TP + col0 + m] = src[m];
             }
             if (jl == 0 && j > 0) {
-                const double *src = a.Sbuf[st_.cur] + (i64)b * a.slice + (i64)(j - 1) * a.pitch + XM_PADL + i0;
+                const double *src = a.Sbuf[cur] + (i64)b * a.slice + (i64)(j - 1) * a.pitch + XM_PADL + i0;
                 #pragma unroll
                 for (int m = 0; m < K; ++m) if (m < nvalid) Tc[-TP + col0 + m] = src[m];
             }
         }
-        cluster.sync();
+        cluster.sync();                    // once per slice: every tile is filled before a neighbour's first push can land
 
+        // The stop test of sweep n is LAGGED by one colour: its norm partials travel through the cluster while colour 0
+        // of sweep n+1 is already being computed (the red cells' old values parked in shared memory); if the test says
+        // "stop", the red cells are restored -- nothing else has changed -- and the slice ends exactly as if it had been
+        // tested right away.
+        bool pending = false;
         for (int sweep = 0; sweep < a.nsweeps; ++sweep) {
-            // ---- y-"extend" rows (numbas.py:284-310): row 0 := row 1, row ny-1 := row ny-2 where != undef ----
+            // ---- y-"extend" rows (numbas.py:284-310): row 0 := row 1, row ny-1 := row ny-2 where != undef.
+            //      Into the tile only (row 1 / ny-2 read it there); the registers follow once the sweep is certain ----
             if (ext_cta) {
                 if (ext_lo || ext_hi) {
                     const double *Tr = ext_lo ? Tn : Ts;
@@ -219,65 +286,127 @@ xc_cluster_kernel(const XcArgs a)
                     sv[K + 1] = Tr[eastIdx];
                     #pragma unroll
                     for (int m = 0; m < K; ++m) {
-                        double s = sv[m + 1];
+                        double v = sv[m + 1];
                         if (!periodic) {
-                            if (i0 + m == 0) s = sv[m + 2];                 // S[0,0] = S[1,1]
-                            if (i0 + m == nx - 1) s = sv[m];                // S[0,nx-1] = S[1,nx-2]
+                            if (i0 + m == 0) v = sv[m + 2];                 // S[0,0] = S[1,1]
+                            if (i0 + m == nx - 1) v = sv[m];                // S[0,nx-1] = S[1,nx-2]
                         }
-                        if (m < nvalid && s != undef) psi[m] = s;
-                        Tc[col0 + m] = psi[m];
+                        Tc[col0 + m] = (m < nvalid && v != undef) ? v : psi[m];
                     }
                 }
                 __syncthreads();                                   // row 1 / ny-2 read the new rows (same CTA)
             }
-            // ---- colour 0, colour 1: one cluster barrier each ----
-            if (par0 == 0) xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, pushN, pushS);
-            else           xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, pushN, pushS);
-            cluster.sync();
-            if (par0 == 0) xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, pushN, pushS);
-            else           xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, pushN, pushS);
-            // ---- sum|psi|, count over psi != undef (numbas.py:1710-1728): thread -> warp -> a slot in every CTA ----
-            double s = 0.0;
-            int n = 0;
-            #pragma unroll
-            for (int m = 0; m < K; ++m) {
-                const double v = psi[m];
-                if (v != undef) { s += fabs(v); n += 1; }          // slots beyond the run hold undef
+            // ---- colour 0 (compute warps)  ||  the stop test of the previous sweep, numbas.py:401-414 (control warp) ----
+            if (ctrl) {
+                if (post && halo_bytes) xf_mbar_expect_tx(hb, halo_bytes);
+                if (pending) {
+                    const unsigned pp = sp - 1u;
+                    xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
+                    double ts = 0.0, tn = 0.0;
+                    {
+                        const double2 *sl = slot + (pp & 1u) * (R * NW);
+                        for (int k = lane; k < R * NW; k += 32) { const double2 v = sl[k]; ts += v.x; tn += v.y; }
+                    }
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+                        tn += __shfl_xor_sync(0xffffffffu, tn, o);
+                    }
+                    xd_decide(st_, ts, (i64)tn, a.tol, a.mxLoop, a.zero_exit);   // the control warps of all CTAs, identically
+                    if (lane == 0) verdict[0] = st_.active;
+                }
+            } else if (upd_row) {
+                if (par0 == 0) {
+                    #pragma unroll
+                    for (int c = 0; c < K / 2; ++c) bkT[c * nth + tid] = psi[2 * c];
+                    xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0]);
+                } else {
+                    #pragma unroll
+                    for (int c = 0; c < K / 2; ++c) bkT[c * nth + tid] = psi[2 * c + 1];
+                    xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0]);
+                }
             }
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                n += __shfl_xor_sync(0xffffffffu, n, o);
+            __syncthreads();
+            if (edgeN || edgeS) xf_mbar_wait(hb, ph0 & 1u);
+            ++ph0;
+            if (pending) {
+                pending = false;
+                if (!verdict[0]) {                                 // undo the red half sweep
+                    if (upd_row) {
+                        if (par0 == 0) {
+                            #pragma unroll
+                            for (int c = 0; c < K / 2; ++c) psi[2 * c] = bkT[c * nth + tid];
+                        } else {
+                            #pragma unroll
+                            for (int c = 0; c < K / 2; ++c) psi[2 * c + 1] = bkT[c * nth + tid];
+                        }
+                    }
+                    break;
+                }
             }
-            if (lane < R) {
-                double *rs = cluster.map_shared_rank(slotS, lane);
-                int *rn = cluster.map_shared_rank(slotN, lane);
-                rs[rank * NW + warp] = s;
-                rn[rank * NW + warp] = n;
+            if (ext_lo || ext_hi) {
+                #pragma unroll
+                for (int m = 0; m < K; ++m) psi[m] = Tc[col0 + m];
             }
-            cluster.sync();
-            double ts = 0.0;
-            i64 tn = 0;
-            for (int k = lane; k < R * NW; k += 32) { ts += slotS[k]; tn += slotN[k]; }
+            // ---- colour 1, and sum|psi| / count over psi != undef (numbas.py:1710-1728): thread -> warp -> a slot in every CTA ----
+            if (post) {
+                xf_mbar_expect_tx(nb + (sp & 1u), norm_bytes);
+                if (halo_bytes) xf_mbar_expect_tx(hb + 1, halo_bytes);
+            }
+            if (upd_row) {
+                if (par0 == 0)
+                    xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1]);
+                else
+                    xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1]);
+            }
+            if (!ctrl) {
+                double s0 = 0.0, s1 = 0.0;
+                int n = 0;
+                #pragma unroll
+                for (int m = 0; m < K; m += 2) {                   // slots beyond the run hold undef
+                    const double v = psi[m], w = psi[m + 1];
+                    if (v != undef) { s0 += fabs(v); n += 1; }
+                    if (w != undef) { s1 += fabs(w); n += 1; }
+                }
+                double sw_ = s0 + s1;
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sw_ += __shfl_xor_sync(0xffffffffu, sw_, o);
+                n = __reduce_add_sync(0xffffffffu, n);
+                if (lane < R)
+                    xc_st_async2(xc_mapa(xf_smem_u32(slot + (sp & 1u) * (R * NW) + rank * NW + warp), lane), sw_, (double)n,
+                                 xc_mapa(xf_smem_u32(nb + (sp & 1u)), lane));
+            }
+            __syncthreads();
+            if (edgeN || edgeS) xf_mbar_wait(hb + 1, ph1 & 1u);
+            ++ph1;
+            pending = true;
+            ++sp;
+        }
+        if (pending && ctrl) {                                     // the sweep budget of this launch is used up: test the last sweep now
+            const unsigned pp = sp - 1u;
+            xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
+            double ts = 0.0, tn = 0.0;
+            {
+                const double2 *sl = slot + (pp & 1u) * (R * NW);
+                for (int k = lane; k < R * NW; k += 32) { const double2 v = sl[k]; ts += v.x; tn += v.y; }
+            }
             #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 ts += __shfl_xor_sync(0xffffffffu, ts, o);
                 tn += __shfl_xor_sync(0xffffffffu, tn, o);
             }
-            xd_decide(st_, ts, tn, a.tol, a.mxLoop, a.zero_exit);  // every thread of the cluster, identically
-            if (!st_.active) break;
+            xd_decide(st_, ts, (i64)tn, a.tol, a.mxLoop, a.zero_exit);
         }
         // ---- psi back to the plan's buffer, state back ----
         if (act) {
-            double *dst = a.Sbuf[st_.cur] + (i64)b * a.slice + (i64)j * a.pitch + XM_PADL + i0;
+            double *dst = a.Sbuf[cur] + (i64)b * a.slice + (i64)j * a.pitch + XM_PADL + i0;
             #pragma unroll
             for (int m = 0; m < K; ++m) if (m < nvalid) dst[m] = psi[m];
         }
-        if (rank == 0 && tid == 0) {
+        if (rank == 0 && post) {
             a.st[b] = st_;
             if (!st_.active) atomicSub(a.nactive, 1);
         }
-        cluster.sync();                                            // nobody writes into a tile that is being refilled
     }
     cluster.sync();                                                // no CTA leaves while its shared memory may be addressed
 }
@@ -365,8 +494,8 @@ static inline bool xc_choose(int ny, int nx, bool periodic, i64 batch, int sm_co
             if (periodic && nx % K != 0) continue;          // the last run ends at column nx-1 (its east neighbour is the ghost)
             const int RPR = (nx + K - 1) / K, WPR = (RPR + 31) / 32;
             const int warps = RPmax * WPR;
-            if (warps * 32 > max_threads[k] || warps > 32) continue;
-            const size_t smem = ((size_t)(RPmax + 2) * (2 + (size_t)WPR * 32 * (K + 1)) + (size_t)R * warps * 2) * 8 + 64;
+            if ((warps + 1) * 32 > max_threads[k] || warps + 1 > 32) continue;     // + the control warp
+            const size_t smem = ((size_t)(RPmax + 2) * (2 + (size_t)WPR * 32 * (K + 1)) + (size_t)R * warps * 4 + (size_t)(K / 2) * (warps + 1) * 32) * 8 + 64;
             if (smem > 200 * 1024) continue;
             const double half = (R > 1 ? 400.0 : 60.0) + 150.0 + (K / 2) * 40.0 * ((warps + 3) / 4);
             const i64 side = sm_count / R;
@@ -416,8 +545,8 @@ static inline int cluster_plan_build(ClusterPlan &cp, const FusedPlan &fp, int s
     a.TP = 2 + a.WPR * 32 * (K + 1);
     a.NW = a.RPmax * a.WPR;
     cp.kind = fp.kind; cp.K = K; cp.R = R;
-    cp.threads = a.NW * 32;
-    cp.smem = ((size_t)(a.RPmax + 2) * a.TP + (size_t)R * a.NW * 2) * sizeof(double) + 64;
+    cp.threads = (a.NW + 1) * 32;                // + the control warp
+    cp.smem = ((size_t)(a.RPmax + 2) * a.TP + (size_t)R * a.NW * 4 + (size_t)(K / 2) * cp.threads) * sizeof(double) + 64;
     int maxcl = 0;
 #define XC_OCC(KD, K_) e = xc_launch<KD, K_>(cp, 0, &maxcl)
     XC_DISPATCH(cp.kind, cp.K, XC_OCC);
