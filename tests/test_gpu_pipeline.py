@@ -35,7 +35,10 @@ def test_pipelined_poisson_front_end_equals_plain_call(gpu_ctx, monkeypatch, dev
     ip2 = dict(ip, devices=devices)
     s2 = xb.invert_Poisson(F, dims=['lat', 'lon'], iParams=ip2)
     assert np.array_equal(s1.values, s2.values, equal_nan=True)
-    assert np.array_equal(ip1['flags_all'], ip2['flags_all'])
+    # loop counts and overflow flags identical; the last relative change to 1e-9: the cluster engine adds the partial
+    # sums of |S| in an order that depends on the cluster shape, which is chosen per call (here: 12 slices vs 2 per chunk)
+    assert np.array_equal(ip1['flags_all'][:, [0, 2]], ip2['flags_all'][:, [0, 2]])
+    assert np.allclose(ip1['flags_all'][:, 1], ip2['flags_all'][:, 1], rtol=1e-9, atol=0)
     assert len(set(ip1['flags_all'][:, 2])) > 1                       # the slices stop at different sweeps
     assert "pipeline" not in ip1['stats'] and ip2['stats']['pipeline']['chunks'] >= 4
     assert ip2['stats']['pipeline']['workers'] == 2

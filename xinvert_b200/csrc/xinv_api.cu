@@ -573,7 +573,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
                 const char *ec = getenv("XINV_CLUSTER");
                 std::string whyc = "disabled by XINV_CLUSTER=0";
                 if (!(ec && atoi(ec) == 0 && o.engine == XINV_ENGINE_AUTO))
-                    cluster_plan_build(pb.cluster, pb.fused, c->sm_count, g, pb.q, pb.batch, whyc);
+                    cluster_plan_build(pb.cluster, pb.fused, c->sm_count, g, pb.q, pb.batch, o.engine == XINV_ENGINE_CLUSTER, whyc);
                 if (!pb.cluster.built && o.engine == XINV_ENGINE_CLUSTER)
                     return set_err(XINV_E_UNSUPPORTED, "cluster engine unavailable: %s", whyc.c_str());
             }

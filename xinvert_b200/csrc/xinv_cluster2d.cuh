@@ -88,6 +88,9 @@ __device__ __forceinline__ void xc_st_async2(uint32_t raddr, double v, double w,
                  ::"r"(raddr), "d"(v), "d"(w), "r"(rbar) : "memory");
 }
 
+// named barrier 1: the compute warps of a CTA among themselves (the control warp is not held up by it, nor they by it)
+__device__ __forceinline__ void xc_compute_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
 // one colour of a thread's run: cells m = PAR, PAR + 2, ... (< K)
 template <int KIND, int K, int PAR>
 __device__ __forceinline__ void xc_half(double (&psi)[K], const double (&fd)[K], const XcRow<KIND> &cr, const XcArgs &a,
@@ -106,30 +109,55 @@ __device__ __forceinline__ void xc_half(double (&psi)[K], const double (&fd)[K],
     double sw = 0.0, se = 0.0;
     if (PAR == 0) sw = Tc[westIdx];
     if (LASTIN) se = Tc[eastIdx];
-    #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        const int m = PAR + 2 * c;
-        const double So = psi[m];
-        const double Sw = (m == 0) ? sw : psi[m > 0 ? m - 1 : 0];
-        const double Se = (m == K - 1) ? se : psi[m < K - 1 ? m + 1 : K - 1];
-        const double Snn = sn[c], Sss = ss[c];
-        double temp;
-        if constexpr (KIND == 0) {
-            const XcRow<0> &r = cr;
-            const double t1 = (r.An * (Snn - So) - r.Ac * (So - Sss)) * a.ratioSqr;
-            const double t4 = (r.C * (Se - So) - r.C * (So - Sw));
-            temp = (t1 + t4) - fd[m];
-            temp = temp * r.fac;
-        } else {
-            const XcRow<1> &g = cr;
-            temp = g.A * ((Snn - So) - (So - Sss)) * a.ratioSqr;
+    // The cells of a colour are independent: the arithmetic is written stage by stage ACROSS the cells so that the
+    // dependent chain of one cell (8 operations deep) is interleaved with the others' (the compiler keeps this order).
+    // Per cell the operations and their order are those of xm_eval / xm_eval_gen (numbas.py:351-369, :1132-1153).
+    double t[NC];
+    if constexpr (KIND == 0) {
+        const XcRow<0> &r = cr;
+        double a1[NC], a2[NC], a3[NC], a4[NC];
+        #pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int m = PAR + 2 * c;
+            const double So = psi[m];
+            const double Sw = (m == 0) ? sw : psi[m > 0 ? m - 1 : 0];
+            const double Se = (m == K - 1) ? se : psi[m < K - 1 ? m + 1 : K - 1];
+            a1[c] = sn[c] - So; a2[c] = So - ss[c]; a3[c] = Se - So; a4[c] = So - Sw;
+        }
+        #pragma unroll
+        for (int c = 0; c < NC; ++c) { a1[c] = r.An * a1[c]; a2[c] = r.Ac * a2[c]; a3[c] = r.C * a3[c]; a4[c] = r.C * a4[c]; }
+        #pragma unroll
+        for (int c = 0; c < NC; ++c) { a1[c] = a1[c] - a2[c]; a3[c] = a3[c] - a4[c]; }
+        #pragma unroll
+        for (int c = 0; c < NC; ++c) a1[c] = a1[c] * a.ratioSqr;
+        #pragma unroll
+        for (int c = 0; c < NC; ++c) t[c] = a1[c] + a3[c];
+        #pragma unroll
+        for (int c = 0; c < NC; ++c) t[c] = t[c] - fd[PAR + 2 * c];
+        #pragma unroll
+        for (int c = 0; c < NC; ++c) t[c] = t[c] * r.fac;
+    } else {
+        const XcRow<1> &g = cr;
+        #pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int m = PAR + 2 * c;
+            const double So = psi[m];
+            const double Sw = (m == 0) ? sw : psi[m > 0 ? m - 1 : 0];
+            const double Se = (m == K - 1) ? se : psi[m < K - 1 ? m + 1 : K - 1];
+            const double Snn = sn[c], Sss = ss[c];
+            double temp = g.A * ((Snn - So) - (So - Sss)) * a.ratioSqr;
             temp = temp + g.C * ((Se - So) - (So - Sw));
             temp = temp + (g.D * (Snn - Sss) * a.ratio + g.E * (Se - Sw)) * a.delx / 2.0;
             temp = temp + (g.F * So - fd[m]) * a.delxSqr;
-            temp = temp * g.fac;
+            t[c] = temp * g.fac;
         }
+    }
+    #pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int m = PAR + 2 * c;
         const bool upd = __double2hiint(fd[m]) != XM_SKIP_HI;
-        psi[m] = upd ? So + temp : So;
+        const double nv = psi[m] + t[c];
+        psi[m] = upd ? nv : psi[m];
     }
     if (act) {
         #pragma unroll
@@ -166,8 +194,8 @@ xc_cluster_kernel(const XcArgs a)
     const bool ctrl = (warp == NW);
     double *T = reinterpret_cast<double *>(xc_smem);                       // [(RPmax + 2)][TP]
     double2 *slot = reinterpret_cast<double2 *>(T + (size_t)(a.RPmax + 2) * TP);   // [2][R * NW]: (sum, count) per compute warp of the cluster
-    double *bkT = reinterpret_cast<double *>(slot + 2 * R * NW);           // [K / 2][threads]: the red cells before a speculative half sweep
-    uint64_t *hb = reinterpret_cast<uint64_t *>(bkT + (size_t)(K / 2) * nth);   // [2] halo values of colour 0 / 1 have arrived
+    double *bkT = reinterpret_cast<double *>(slot + 2 * R * NW);           // [K][threads]: every cell's value before a speculative sweep
+    uint64_t *hb = reinterpret_cast<uint64_t *>(bkT + (size_t)K * nth);   // [2] halo values of colour 0 / 1 have arrived
     uint64_t *nb = hb + 2;                                                 // [2] norm partials have arrived (by parity of the sweep)
     int *verdict = reinterpret_cast<int *>(nb + 2);                        // [1] "the slice goes on", written by the control warp
     if (tid == 0) {
@@ -218,8 +246,10 @@ xc_cluster_kernel(const XcArgs a)
     const bool ext_hi = act && a.bcy == XD_BC_EXTEND && j == ny - 1;
     const bool ext_cta = a.bcy == XD_BC_EXTEND && (rank == 0 || rank == R - 1);
     const bool post = ctrl && lane == 0;                          // the thread that posts transaction counts
+    // (Letting the first / last row's warps go first in a half sweep -- a named barrier holding the interior warps back
+    // until the pushes are on their way -- was measured slower: 2.87 vs 2.13 us per sweep on 360 x 180.)
     unsigned sp = 0;                                              // completed sweeps so far: which norm barrier, which parity
-    unsigned ph0 = 0, ph1 = 0;                                    // phases of the two halo barriers so far (a sweep that is undone has used hb[0] only)
+    unsigned ph = 0;                                              // sweeps so far: parity of the two halo barriers
 
     for (int b = cid; b < a.batch; b += ncl) {
         if (!a.st[b].active) continue;                            // the same for every thread of the cluster
@@ -268,38 +298,18 @@ xc_cluster_kernel(const XcArgs a)
         }
         cluster.sync();                    // once per slice: every tile is filled before a neighbour's first push can land
 
-        // The stop test of sweep n is LAGGED by one colour: its norm partials travel through the cluster while colour 0
-        // of sweep n+1 is already being computed (the red cells' old values parked in shared memory); if the test says
-        // "stop", the red cells are restored -- nothing else has changed -- and the slice ends exactly as if it had been
-        // tested right away.
+        // The stop test of sweep n is LAGGED by one sweep: its norm partials travel through the cluster and are added up
+        // and judged by the control warp while the compute warps are already busy with sweep n+1, every cell's old value
+        // parked in shared memory; if the verdict is "stop", the cells are restored and the slice ends exactly as if it
+        // had been tested right away (numbas.py:401-414: fields, flags and loop counts are unchanged by the lag).
         bool pending = false;
         for (int sweep = 0; sweep < a.nsweeps; ++sweep) {
-            // ---- y-"extend" rows (numbas.py:284-310): row 0 := row 1, row ny-1 := row ny-2 where != undef.
-            //      Into the tile only (row 1 / ny-2 read it there); the registers follow once the sweep is certain ----
-            if (ext_cta) {
-                if (ext_lo || ext_hi) {
-                    const double *Tr = ext_lo ? Tn : Ts;
-                    double sv[K + 2];
-                    sv[0] = Tr[westIdx];
-                    #pragma unroll
-                    for (int m = 0; m < K; ++m) sv[m + 1] = Tr[col0 + m];
-                    sv[K + 1] = Tr[eastIdx];
-                    #pragma unroll
-                    for (int m = 0; m < K; ++m) {
-                        double v = sv[m + 1];
-                        if (!periodic) {
-                            if (i0 + m == 0) v = sv[m + 2];                 // S[0,0] = S[1,1]
-                            if (i0 + m == nx - 1) v = sv[m];                // S[0,nx-1] = S[1,nx-2]
-                        }
-                        Tc[col0 + m] = (m < nvalid && v != undef) ? v : psi[m];
-                    }
-                }
-                __syncthreads();                                   // row 1 / ny-2 read the new rows (same CTA)
-            }
-            // ---- colour 0 (compute warps)  ||  the stop test of the previous sweep, numbas.py:401-414 (control warp) ----
             if (ctrl) {
-                if (post && halo_bytes) xf_mbar_expect_tx(hb, halo_bytes);
-                if (pending) {
+                if (post) {
+                    if (halo_bytes) { xf_mbar_expect_tx(hb, halo_bytes); xf_mbar_expect_tx(hb + 1, halo_bytes); }
+                    xf_mbar_expect_tx(nb + (sp & 1u), norm_bytes);
+                }
+                if (pending) {                                     // the stop test of the previous sweep
                     const unsigned pp = sp - 1u;
                     xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
                     double ts = 0.0, tn = 0.0;
@@ -315,51 +325,48 @@ xc_cluster_kernel(const XcArgs a)
                     xd_decide(st_, ts, (i64)tn, a.tol, a.mxLoop, a.zero_exit);   // the control warps of all CTAs, identically
                     if (lane == 0) verdict[0] = st_.active;
                 }
-            } else if (upd_row) {
-                if (par0 == 0) {
-                    #pragma unroll
-                    for (int c = 0; c < K / 2; ++c) bkT[c * nth + tid] = psi[2 * c];
-                    xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0]);
-                } else {
-                    #pragma unroll
-                    for (int c = 0; c < K / 2; ++c) bkT[c * nth + tid] = psi[2 * c + 1];
-                    xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0]);
-                }
-            }
-            __syncthreads();
-            if (edgeN || edgeS) xf_mbar_wait(hb, ph0 & 1u);
-            ++ph0;
-            if (pending) {
-                pending = false;
-                if (!verdict[0]) {                                 // undo the red half sweep
-                    if (upd_row) {
-                        if (par0 == 0) {
-                            #pragma unroll
-                            for (int c = 0; c < K / 2; ++c) psi[2 * c] = bkT[c * nth + tid];
-                        } else {
-                            #pragma unroll
-                            for (int c = 0; c < K / 2; ++c) psi[2 * c + 1] = bkT[c * nth + tid];
+                if (halo_bytes) xf_mbar_wait(hb, ph & 1u);         // (a barrier is armed again only after its phase is over)
+            } else {
+                #pragma unroll
+                for (int m = 0; m < K; ++m) bkT[m * nth + tid] = psi[m];
+                // ---- y-"extend" rows (numbas.py:284-310): row 0 := row 1, row ny-1 := row ny-2 where != undef ----
+                if (ext_cta) {
+                    if (ext_lo || ext_hi) {
+                        const double *Tr = ext_lo ? Tn : Ts;
+                        double sv[K + 2];
+                        sv[0] = Tr[westIdx];
+                        #pragma unroll
+                        for (int m = 0; m < K; ++m) sv[m + 1] = Tr[col0 + m];
+                        sv[K + 1] = Tr[eastIdx];
+                        #pragma unroll
+                        for (int m = 0; m < K; ++m) {
+                            double v = sv[m + 1];
+                            if (!periodic) {
+                                if (i0 + m == 0) v = sv[m + 2];             // S[0,0] = S[1,1]
+                                if (i0 + m == nx - 1) v = sv[m];            // S[0,nx-1] = S[1,nx-2]
+                            }
+                            if (m < nvalid && v != undef) psi[m] = v;
+                            Tc[col0 + m] = psi[m];
                         }
                     }
-                    break;
+                    xc_compute_sync(NW * 32);                      // row 1 / ny-2 read the new rows (same CTA)
                 }
-            }
-            if (ext_lo || ext_hi) {
-                #pragma unroll
-                for (int m = 0; m < K; ++m) psi[m] = Tc[col0 + m];
-            }
-            // ---- colour 1, and sum|psi| / count over psi != undef (numbas.py:1710-1728): thread -> warp -> a slot in every CTA ----
-            if (post) {
-                xf_mbar_expect_tx(nb + (sp & 1u), norm_bytes);
-                if (halo_bytes) xf_mbar_expect_tx(hb + 1, halo_bytes);
-            }
-            if (upd_row) {
-                if (par0 == 0)
-                    xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1]);
-                else
-                    xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1]);
-            }
-            if (!ctrl) {
+                // ---- colour 0 ----
+                if (upd_row) {
+                    if (par0 == 0)
+                        xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0]);
+                    else
+                        xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0]);
+                }
+                xc_compute_sync(NW * 32);
+                if (edgeN || edgeS) xf_mbar_wait(hb, ph & 1u);
+                // ---- colour 1, and sum|psi| / count over psi != undef (numbas.py:1710-1728): thread -> warp -> a slot in every CTA ----
+                if (upd_row) {
+                    if (par0 == 0)
+                        xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1]);
+                    else
+                        xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1]);
+                }
                 double s0 = 0.0, s1 = 0.0;
                 int n = 0;
                 #pragma unroll
@@ -377,10 +384,21 @@ xc_cluster_kernel(const XcArgs a)
                                  xc_mapa(xf_smem_u32(nb + (sp & 1u)), lane));
             }
             __syncthreads();
-            if (edgeN || edgeS) xf_mbar_wait(hb + 1, ph1 & 1u);
-            ++ph1;
-            pending = true;
+            if (edgeN || edgeS || (ctrl && halo_bytes)) xf_mbar_wait(hb + 1, ph & 1u);
+            ++ph;
             ++sp;
+            if (pending && !verdict[0]) {                          // the previous sweep was the last one: undo this one
+                if (ctrl) {
+                    const unsigned pp = sp - 1u;                   // its partials are on their way: let them land
+                    xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
+                } else {
+                    #pragma unroll
+                    for (int m = 0; m < K; ++m) psi[m] = bkT[m * nth + tid];
+                }
+                pending = false;
+                break;
+            }
+            pending = true;
         }
         if (pending && ctrl) {                                     // the sweep budget of this launch is used up: test the last sweep now
             const unsigned pp = sp - 1u;
@@ -474,62 +492,79 @@ static cudaError_t xc_launch(const ClusterPlan &p, cudaStream_t stream, int *max
     return cudaLaunchKernelEx(&cfg, xc_cluster_kernel<KIND, K>, p.args);
 }
 
-// Pick (R, K) for a slice of ny x nx and a batch; returns false when no shape fits.
-// Model of one half sweep (cycles): a cluster barrier, a fixed part, and the updates of one colour --
-// K/2 cells per thread, ~40 issue cycles of FP64 work per cell and warp, the warps of an SM sub-partition one
-// after the other.  Over the batch: clusters run side by side, floor(SMs / R) at a time.
-static inline bool xc_choose(int ny, int nx, bool periodic, i64 batch, int sm_count, const int *max_threads /*[XC_NK]*/,
-                             int *R_out, int *K_out)
+// Fill the shape-dependent fields of a plan for cluster size R and run length K; false when the shape does not fit.
+static inline bool xc_shape(ClusterPlan &cp, const XdGeom &g, int R, int K, int max_threads)
 {
-    const char *eR = getenv("XINV_CLUSTER_R"), *eK = getenv("XINV_CLUSTER_K");
-    double best = 1e300;
-    bool found = false;
-    for (int R = 16; R >= 1; R >>= 1) {
-        if (eR && atoi(eR) != R) continue;
-        if (ny / R < 2 && R > 1) continue;                  // every CTA holds at least two rows (y-extend stays inside a CTA)
-        const int RPmax = (ny + R - 1) / R;
-        for (int k = 0; k < XC_NK; ++k) {
-            const int K = XC_KS[k];
-            if (eK && atoi(eK) != K) continue;
-            if (periodic && nx % K != 0) continue;          // the last run ends at column nx-1 (its east neighbour is the ghost)
-            const int RPR = (nx + K - 1) / K, WPR = (RPR + 31) / 32;
-            const int warps = RPmax * WPR;
-            if ((warps + 1) * 32 > max_threads[k] || warps + 1 > 32) continue;     // + the control warp
-            const size_t smem = ((size_t)(RPmax + 2) * (2 + (size_t)WPR * 32 * (K + 1)) + (size_t)R * warps * 4 + (size_t)(K / 2) * (warps + 1) * 32) * 8 + 64;
-            if (smem > 200 * 1024) continue;
-            const double half = (R > 1 ? 400.0 : 60.0) + 150.0 + (K / 2) * 40.0 * ((warps + 3) / 4);
-            const i64 side = sm_count / R;
-            const double waves = (double)((batch + side - 1) / side);
-            const double cost = half * waves;
-            if (cost < best) { best = cost; *R_out = R; *K_out = K; found = true; }
-        }
-    }
-    return found;
+    const int ny = (int)g.ny, nx = (int)g.nx;
+    if (R > 1 && ny / R < 2) return false;                  // every CTA holds at least two rows (y-extend stays inside a CTA)
+    if (g.bcx == XD_BC_PERIODIC && nx % K != 0) return false;   // the last run ends at column nx-1 (its east neighbour is the ghost)
+    XcArgs &a = cp.args;
+    a.R = R;
+    a.RPR = (nx + K - 1) / K;
+    a.WPR = (a.RPR + 31) / 32;
+    a.RPmax = (ny + R - 1) / R;
+    a.TP = 2 + a.WPR * 32 * (K + 1);
+    a.NW = a.RPmax * a.WPR;
+    if ((a.NW + 1) * 32 > max_threads || a.NW + 1 > 32) return false;       // + the control warp
+    cp.K = K; cp.R = R;
+    cp.threads = (a.NW + 1) * 32;
+    cp.smem = ((size_t)(a.RPmax + 2) * a.TP + (size_t)R * a.NW * 4 + (size_t)K * cp.threads) * sizeof(double) + 64;
+    return cp.smem <= 200 * 1024;
 }
 
 // Build on top of a fused plan with row coefficients (p.rc): same operands, another way through them.
+// (R, K) by a cost model fitted to measurements on B200 (scripts/bench_cluster_batch.py, scripts/prof_c1.py):
+//   one sweep of a cluster ~ 2 x [550 + 70 (K/2) ceil(warps / 4)] cycles  (DSMEM flight + CTA barrier + stop-test share;
+//                                                                          K/2 cells per thread and colour, the warps of
+//                                                                          an SM sub-partition one after the other)
+//   a batch takes ceil(batch / clusters resident at once) such sweeps;
+//   the marching engine ~ 5 us + cells / 2.6e5 per us  (its fixed cost per pass, then 2.6e11 cell-updates/s).
+// `force`: engine = 'cluster' was asked for -- take the best shape even where the marching engine is expected to win.
 static inline int cluster_plan_build(ClusterPlan &cp, const FusedPlan &fp, int sm_count, const XdGeom &g, const XdCoef &q,
-                                     i64 batch, std::string &why)
+                                     i64 batch, bool force, std::string &why)
 {
+    (void)sm_count;
     cluster_plan_release(cp);
     if (!fp.built || !fp.rc) { why = "cluster engine needs coefficients constant along x"; return -1; }
     const XmArgs &fa = fp.args;
-    const bool periodic = (g.bcx == XD_BC_PERIODIC);
-    int max_threads[XC_NK];
+    const char *eR = getenv("XINV_CLUSTER_R"), *eK = getenv("XINV_CLUSTER_K");
     cudaError_t e = cudaSuccess;
+    ClusterPlan best;
+    double best_us = 1e300;
     for (int k = 0; k < XC_NK; ++k) {
+        const int K = XC_KS[k];
+        if (eK && atoi(eK) != K) continue;
         int mt = 0;
 #define XC_ATTR(KD, K_) e = xc_attr<KD, K_>(200 * 1024, 16, &mt)
-        XC_DISPATCH(fp.kind, XC_KS[k], XC_ATTR);
+        XC_DISPATCH(fp.kind, K, XC_ATTR);
 #undef XC_ATTR
         if (e != cudaSuccess) { why = std::string("cluster kernel attributes: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return -1; }
-        max_threads[k] = mt;
+        for (int R = 16; R >= 1; R >>= 1) {
+            if (eR && atoi(eR) != R) continue;
+            ClusterPlan c;
+            c.kind = fp.kind;
+            if (!xc_shape(c, g, R, K, mt)) continue;
+            int maxcl = 0;
+#define XC_OCC(KD, K_) e = xc_launch<KD, K_>(c, 0, &maxcl)
+            XC_DISPATCH(c.kind, c.K, XC_OCC);
+#undef XC_OCC
+            if (e != cudaSuccess || maxcl < 1) { (void)cudaGetLastError(); continue; }
+            const i64 waves = (batch + maxcl - 1) / maxcl;
+            const double half = (R > 1 ? 550.0 : 250.0) + 70.0 * (K / 2) * ((c.args.NW + 3) / 4);
+            const double us = (double)waves * 2.0 * half / 1900.0;
+            if (us < best_us) {
+                best_us = us; best = c;
+                best.grid = (int)((batch < maxcl ? batch : maxcl) * R);
+            }
+        }
     }
-    int R = 1, K = 4;
-    if (!xc_choose((int)g.ny, (int)g.nx, periodic, batch, sm_count, max_threads, &R, &K)) {
-        why = "slice does not fit a thread-block cluster";
+    if (best_us >= 1e300) { why = "slice does not fit a thread-block cluster"; return -1; }
+    const double march_us = 5.0 + (double)g.N * (double)batch / 2.6e5;
+    if (!force && !(eR || eK) && best_us >= march_us) {
+        why = "the marching engine is expected to be faster for this batch";
         return -1;
     }
+    cp = best;
     XcArgs &a = cp.args;
     a.Sbuf[0] = fa.Sbuf[0]; a.Sbuf[1] = fa.Sbuf[1];
     a.Fd = (const double *)fp.bufFd; a.rows = (const double *)fp.bufRow;
@@ -538,27 +573,6 @@ static inline int cluster_plan_build(ClusterPlan &cp, const FusedPlan &fp, int s
     a.bcy = g.bcy; a.bcx = g.bcx;
     a.cbFd = fa.cbFd; a.cbRow = fa.cbRow;
     a.ratioSqr = fa.ratioSqr; a.undef = q.undef; a.ratio = fa.ratio; a.delx = fa.delx; a.delxSqr = fa.delxSqr;
-    a.R = R;
-    a.RPR = (int)((g.nx + K - 1) / K);
-    a.WPR = (a.RPR + 31) / 32;
-    a.RPmax = (int)((g.ny + R - 1) / R);
-    a.TP = 2 + a.WPR * 32 * (K + 1);
-    a.NW = a.RPmax * a.WPR;
-    cp.kind = fp.kind; cp.K = K; cp.R = R;
-    cp.threads = (a.NW + 1) * 32;                // + the control warp
-    cp.smem = ((size_t)(a.RPmax + 2) * a.TP + (size_t)R * a.NW * 4 + (size_t)(K / 2) * cp.threads) * sizeof(double) + 64;
-    int maxcl = 0;
-#define XC_OCC(KD, K_) e = xc_launch<KD, K_>(cp, 0, &maxcl)
-    XC_DISPATCH(cp.kind, cp.K, XC_OCC);
-#undef XC_OCC
-    if (e != cudaSuccess || maxcl < 1) {
-        why = std::string("no cluster of ") + std::to_string(R) + " CTAs can be resident: " + cudaGetErrorString(e);
-        (void)cudaGetLastError();
-        cluster_plan_release(cp);
-        return -1;
-    }
-    const i64 ncl = batch < maxcl ? batch : maxcl;
-    cp.grid = (int)(ncl * R);
     cp.built = true;
     return 0;
 }
