@@ -55,6 +55,9 @@ extern "C" {
 #define XINV_ENGINE_RESIDENT 3 /* small 2-D slices: the whole solve in one CTA, operands in shared memory */
 #define XINV_ENGINE_CLUSTER 4 /* 2-D, B==0, row coefficients: the whole solve in one thread-block cluster (psi in registers + DSMEM) */
 
+#define XINV_ACCEL_NONE      0
+#define XINV_ACCEL_CHEBYSHEV 1
+
 /* error codes */
 #define XINV_OK          0
 #define XINV_E_ARG      -1    /* bad argument                                           */
@@ -80,6 +83,13 @@ typedef struct xinv_opts {
      * as the reference materialises them); 0 = one slice shared by the whole
      * batch (what xarray broadcasting of time-independent coefficients means). */
     int64_t coef_stride[8];
+    /* Convergence acceleration (NOT in the reference, off by default): XINV_ACCEL_CHEBYSHEV varies the
+     * relaxation factor from half sweep to half sweep -- omega_0 = 1, omega_1 = 1/(1 - rho^2/2),
+     * omega_{h+1} = 1/(1 - rho^2 omega_h/4) -> optArg, with rho^2 = 1 - (2/optArg - 1)^2 the squared Jacobi spectral
+     * radius that optArg is the optimal SOR factor of -- instead of using optArg from the first sweep on.  Colour
+     * ordering only; runs on the cluster, resident and colour engines. */
+    int32_t accel;            /* XINV_ACCEL_*                                            */
+    int32_t reserved_;
 } xinv_opts;
 
 /* Statistics of the last solve on a ctx. */

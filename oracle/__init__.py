@@ -20,7 +20,8 @@ import numpy as np
 from .build import build as _build
 
 _BC = {"fixed": 0, "extend": 1, "periodic": 2}
-_ORD = {"lexicographic": 0, "lex": 0, "colour": 1, "color": 1, "redblack": 1}
+_ORD = {"lexicographic": 0, "lex": 0, "colour": 1, "color": 1, "redblack": 1,
+        "chebyshev": 2}      # colour ordering + the Chebyshev schedule of the relaxation factor (xinv.h, xinv_opts.accel)
 
 _lib = None
 

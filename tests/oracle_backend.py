@@ -19,6 +19,13 @@ def _pick(a, b, core):
     return a if a.shape == core else a.reshape((-1,) + core)[b]
 
 
+def _ord(ordering, kw):
+    """iParams['accel'] = 'chebyshev' -> the oracle's colour ordering with the same schedule of the relaxation factor."""
+    if kw.get("accel") == "chebyshev" and ordering in ("colour", "color", "redblack"):
+        return "chebyshev"
+    return ordering
+
+
 def _b_or_none(B):
     return None if (B is None or not np.any(B)) else B
 
@@ -33,7 +40,7 @@ def solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, opt
         fl = np.array(flags, dtype=np.float64).reshape(-1)[:3].copy()
         oracle.invert_standard_2D(Sv[b], _pick(A, b, core), _pick(B, b, core), _pick(C_, b, core), _pick(F, b, core),
                                   core[0], core[1], 0.0, 0.0, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg, undef,
-                                  fl, mxLoop, tolerance, ordering=ordering)
+                                  fl, mxLoop, tolerance, ordering=_ord(ordering, kw))
         out[b] = fl
     return out, {"engine": "oracle"}
 
@@ -48,7 +55,7 @@ def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ra
         fl = np.array(flags, dtype=np.float64).reshape(-1)[:3].copy()
         oracle.invert_general_2D(Sv[b], *[_pick(x, b, core) for x in (A, B, C_, D, E, F, G)], core[0], core[1],
                                  0.0, delx, BCy, BCx, delxSqr, ratio, ratioQtr, ratioSqr, optArg, undef, fl,
-                                 mxLoop, tolerance, ordering=ordering)
+                                 mxLoop, tolerance, ordering=_ord(ordering, kw))
         out[b] = fl
     return out, {"engine": "oracle"}
 
@@ -62,6 +69,6 @@ def solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1S
         fl = np.array(flags, dtype=np.float64).reshape(-1)[:3].copy()
         oracle.invert_standard_3D(Sv[b], *[_pick(x, b, core) for x in (A, B, C_, F)], core[0], core[1], core[2],
                                   0.0, 0.0, 0.0, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1Sqr, optArg, undef, fl,
-                                  mxLoop, tolerance, ordering=ordering)
+                                  mxLoop, tolerance, ordering=_ord(ordering, kw))
         out[b] = fl
     return out, {"engine": "oracle"}

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_opts_struct_layout_matches_header():
     # int32 x6 + int64 x8
-    assert ctypes.sizeof(_lib.XinvOpts) == 6 * 4 + 8 * 8
+    assert ctypes.sizeof(_lib.XinvOpts) == 6 * 4 + 8 * 8 + 2 * 4
     o = _lib.make_opts(ordering="lex", engine="fused", coef_strides=[0, -1, 5])
     assert (o.ordering, o.engine, o.coef_stride[0], o.coef_stride[1], o.coef_stride[2], o.coef_stride[7]) == \
         (1, 2, 0, -1, 5, -1)

@@ -493,7 +493,7 @@ def _poisson_device_front(F, dims, coords, icbc, mParams, iParams):
         S, flags, stats = _device_solvers.solve_standard_2D_rows(
             g.values, A_rows, C_rows, scale, ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1], ip['del1Sqr'],
             ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp, ip['flags'], ip['mxLoop'], ip['tolerance'],
-            ctx=ip.get('ctx'), devices=ip.get('devices'))
+            ctx=ip.get('ctx'), devices=ip.get('devices'), accel=ip.get('accel'))
     except XinvError as e:
         if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
             return None
@@ -635,7 +635,7 @@ def _general_device_front(rows_func, valid, F, dims, coords, icbc, mParams, iPar
         S, flags, stats = _device_solvers.solve_general_2D_rows(
             g.values, rows, r['g_mode'], r['g_p1'], r['g_p2'], ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1],
             ip['del1'], ip['del1Sqr'], ip['ratio'], ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp,
-            ip['flags'], ip['mxLoop'], ip['tolerance'], ctx=ip.get('ctx'), devices=ip.get('devices'))
+            ip['flags'], ip['mxLoop'], ip['tolerance'], ctx=ip.get('ctx'), devices=ip.get('devices'), accel=ip.get('accel'))
     except XinvError as e:
         if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
             return None
@@ -699,7 +699,7 @@ def _omega_device_front(F, dims, coords, icbc, mParams, iParams):
         S, flags, stats = _device_solvers.solve_standard_3D_rows(
             g.values, rows, nv, strides, ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1], ip['BCs'][2], ip['del1Sqr'],
             ip['ratio2Sqr'], ip['ratio1Sqr'], ip['optArg'], _undeftmp, ip['flags'], ip['mxLoop'], ip['tolerance'],
-            ctx=ip.get('ctx'), devices=ip.get('devices'))
+            ctx=ip.get('ctx'), devices=ip.get('devices'), accel=ip.get('accel'))
     except XinvError as e:
         if e.code == E_UNSUPPORTED:              # not a problem for the fused engine
             return None

@@ -103,7 +103,7 @@ def _finish(S, result, order, iParams, labels, flags, stats=None):
 
 
 def _engine_kw(iParams):
-    return dict(ordering=iParams.get("ordering", "colour"), engine=iParams.get("engine", "auto"),
+    return dict(ordering=iParams.get("ordering", "colour"), engine=iParams.get("engine", "auto"), accel=iParams.get("accel"),
                 ctx=iParams.get("ctx"), devices=iParams.get("devices"))
 
 

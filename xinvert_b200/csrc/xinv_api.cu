@@ -15,6 +15,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -85,6 +86,11 @@ struct Problem {
     ResidentPlan resident{};     // small 2-D slices (xinv_resident.cuh)
     ClusterPlan cluster{};       // small / medium 2-D slices with row coefficients, on top of `fused` (xinv_cluster2d.cuh)
     bool front = false;          // xinv_std2d_rows: S is output only, de-masked on the device
+    int accel = 0;               // XINV_ACCEL_*
+    double rho2 = 0.0;           // Chebyshev: squared Jacobi spectral radius implied by optArg
+    double optArg0 = 0.0;        // the caller's optArg (q.optArg is overwritten per half sweep on the colour engine)
+    double omega = 1.0;          // colour engine: factor of the next half sweep (all active slices are at the same sweep)
+    bool omega_first = true;
 };
 
 struct xinv_ctx {
@@ -306,6 +312,7 @@ __global__ void xd_init_state_kernel(XdSliceState *st, const double *flags_in, i
     s.nit = nit0;
     s.redo = 0;
     s.pad_ = 0;
+    s.omega = 1.0;
     st[b] = s;
 }
 
@@ -361,6 +368,9 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     }
     if (o.ordering != XINV_ORDER_COLOUR && o.ordering != XINV_ORDER_LEX) return set_err(XINV_E_ARG, "bad ordering");
     if (o.mem_space != XINV_MEM_HOST && o.mem_space != XINV_MEM_DEVICE) return set_err(XINV_E_ARG, "bad mem_space");
+    if (o.accel != XINV_ACCEL_NONE && o.accel != XINV_ACCEL_CHEBYSHEV) return set_err(XINV_E_ARG, "bad accel");
+    if (o.accel && o.ordering != XINV_ORDER_COLOUR) return set_err(XINV_E_UNSUPPORTED, "accel needs the colour ordering");
+    if (o.accel && (o.engine == XINV_ENGINE_FUSED)) return set_err(XINV_E_UNSUPPORTED, "accel runs on the cluster, resident and colour engines");
 
     CK(cudaSetDevice(c->device));
     Problem &pb = c->pb;
@@ -393,6 +403,16 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     for (int m = 0; m < 6; ++m) pb.q.p[m] = a.p[m];
     pb.q.optArg = a.optArg;
     pb.q.undef = a.undef;
+    pb.accel = o.accel;
+    pb.optArg0 = a.optArg;
+    pb.omega = 1.0;
+    pb.omega_first = true;
+    {   // optArg = 2 / (1 + sqrt(1 - rho^2))  <=>  rho^2 = 1 - (2 / optArg - 1)^2
+        double t = 2.0 / a.optArg - 1.0;
+        t = 1.0 - t * t;
+        pb.rho2 = (t > 0.0 && t < 1.0) ? t : 0.0;       // optArg outside (1, 2): no acceleration (omega stays 1 -> optArg is never reached)
+        if (o.accel && !(a.optArg > 1.0 && a.optArg < 2.0)) return set_err(XINV_E_ARG, "accel needs 1 < optArg < 2");
+    }
 
     memset(&c->stats, 0, sizeof c->stats);
     c->stats.ncolours = g.ncol;
@@ -556,6 +576,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
         if (pb.kind == XD_STD3D) {
             const char *e3 = getenv("XINV_FUSED3");
             if (e3 && atoi(e3) == 0) why = "disabled by XINV_FUSED3=0";
+            else if (pb.accel) why = "accel runs on the colour engine for 3-D problems";
             else if (fused3_plan_supported(g, why) &&
                      fused3_plan_build(pb.fused3, c->xm_work, c->sm_count, g, pb.q, pb.batch, pb.dS, c->stream, why,
                                        a.front ? &front3 : nullptr) == 0)
@@ -573,9 +594,14 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
                 const char *ec = getenv("XINV_CLUSTER");
                 std::string whyc = "disabled by XINV_CLUSTER=0";
                 if (!(ec && atoi(ec) == 0 && o.engine == XINV_ENGINE_AUTO))
-                    cluster_plan_build(pb.cluster, pb.fused, c->sm_count, g, pb.q, pb.batch, o.engine == XINV_ENGINE_CLUSTER, whyc);
+                    cluster_plan_build(pb.cluster, pb.fused, c->sm_count, g, pb.q, pb.batch, o.engine == XINV_ENGINE_CLUSTER || pb.accel, whyc);
                 if (!pb.cluster.built && o.engine == XINV_ENGINE_CLUSTER)
                     return set_err(XINV_E_UNSUPPORTED, "cluster engine unavailable: %s", whyc.c_str());
+            }
+            if (rc == 0 && pb.accel && !pb.cluster.built) {          // the marching kernels have the factor baked in
+                fused_plan_release(pb.fused);
+                pb.engine = XINV_ENGINE_COLOUR;
+                if (a.front) return set_err(XINV_E_UNSUPPORTED, "accel: the device front end needs the cluster engine here");
             }
         } else if (o.engine == XINV_ENGINE_FUSED || o.engine == XINV_ENGINE_CLUSTER) {
             return set_err(XINV_E_UNSUPPORTED, "fused engine unavailable: %s", why.c_str());
@@ -684,7 +710,11 @@ static int sweep_colour_engine(xinv_ctx *c, Problem &pb)
     const int base = (g.scheme == 4) ? 4 : 2;
     if (rows > 0 && g.i1 > g.i0) {
         prof_mark(c, pb);
+        double w1 = pb.omega;
+        if (pb.accel) w1 = xd_cheb_next(pb.omega, pb.rho2, pb.omega_first);
         for (int col = 0; col < g.ncol; ++col) {
+            // Chebyshev: the first half of the colours with omega_h, the second half (and the wrap-fix colours) with omega_h+1
+            if (pb.accel) pb.q.optArg = (col < base / 2) ? pb.omega : w1;
             int nxblk;
             if (col >= base) nxblk = 1;
             else nxblk = (int)(((g.nx + 1) / 2 + XD_SWEEP_THREADS - 1) / XD_SWEEP_THREADS);
@@ -695,6 +725,7 @@ static int sweep_colour_engine(xinv_ctx *c, Problem &pb)
             c->stats.kernel_launches++;
         }
         prof_mark(c, pb);
+        if (pb.accel) { pb.omega = xd_cheb_next(w1, pb.rho2, false); pb.omega_first = false; }
     }
     dim3 ngrid((unsigned)pb.nblk_norm, (unsigned)pb.batch, 1);
     xd_norm_decide_kernel<<<ngrid, XD_NORM_THREADS, 0, c->stream>>>(
@@ -748,12 +779,12 @@ extern "C" int xinv_step(xinv_ctx *c, int64_t sweeps, int64_t *n_active_out)
         else if (pb.engine == XINV_ENGINE_RESIDENT) {
             did = sweeps - it;                                                   // the whole chunk in one launch
             rc = resident_sweep(pb.resident, c->stream, (XdSliceState *)c->state.p, (int *)c->nactive.p, pb.tol, pb.mxLoop,
-                                pb.zero_exit, (int)did, &c->stats.kernel_launches);
+                                pb.zero_exit, (int)did, pb.accel, pb.rho2, &c->stats.kernel_launches);
             if (rc) return set_err(XINV_E_CUDA, "resident engine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (pb.cluster.built) {
             did = sweeps - it;                                                   // the whole chunk in one launch
             rc = cluster_sweep(pb.cluster, c->stream, (XdSliceState *)c->state.p, (int *)c->nactive.p, pb.tol, pb.mxLoop,
-                               pb.zero_exit, (int)did, &c->stats.kernel_launches);
+                               pb.zero_exit, (int)did, pb.accel, pb.rho2, &c->stats.kernel_launches);
             if (rc) return set_err(XINV_E_CUDA, "cluster engine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (f3) {
             did = sweeps - it < pb.fused3.ppl ? sweeps - it : pb.fused3.ppl;     // passes in this launch
@@ -853,13 +884,23 @@ extern "C" int xinv_end(xinv_ctx *c)
     return XINV_OK;
 }
 
+// One sweep loop at a time per device.  Several contexts of one GPU exist so that the copies of one chunk of a batch
+// run under the solve of another (solvers._execute); their sweep loops must not interleave: a loop is a sequence of
+// (cooperative, whole-GPU) launches with a host poll in between, and two of them taking turns launch by launch both
+// finish late -- the chunk whose result should be on its way to the host is still iterating (measured on C5,
+// 3 chunks over 2 contexts: 25.2 ms per step interleaved against 21 ms with the loops one after the other).
+static std::mutex g_solve_mutex[64];
+
 static int run_to_completion(xinv_ctx *c)
 {
     int64_t na = 1;
     int rc = XINV_OK;
-    while (na > 0) {
-        rc = xinv_step(c, 0, &na);
-        if (rc) break;
+    {
+        std::lock_guard<std::mutex> turn(g_solve_mutex[(unsigned)c->device % 64u]);
+        while (na > 0) {
+            rc = xinv_step(c, 0, &na);
+            if (rc) break;
+        }
     }
     int rc2 = xinv_end(c);
     return rc ? rc : rc2;

@@ -59,6 +59,8 @@ struct XcArgs {
     int RPmax;                // rows of the tile besides the two halo rows (= max rows per CTA)
     int TP;                   // tile pitch (doubles)
     int NW;                   // warps per CTA
+    int accel;                // XINV_ACCEL_CHEBYSHEV: omega varies from half sweep to half sweep (xinv.h)
+    double rho2;
 };
 
 template <int KIND> struct XcRow;
@@ -96,7 +98,7 @@ template <int KIND, int K, int PAR>
 __device__ __forceinline__ void xc_half(double (&psi)[K], const double (&fd)[K], const XcRow<KIND> &cr, const XcArgs &a,
                                         double *Tc, const double *Tn, const double *Ts, int col0, int westIdx, int eastIdx,
                                         bool act, bool ghostE, bool ghostW, int ghostEidx,
-                                        uint32_t rN, uint32_t rbN, uint32_t rS, uint32_t rbS)
+                                        uint32_t rN, uint32_t rbN, uint32_t rS, uint32_t rbS, double fac)
 {
     constexpr int NC = (K - PAR + 1) / 2;
     constexpr bool LASTIN = ((K - 1 - PAR) % 2) == 0;          // is cell K-1 of this colour?
@@ -135,7 +137,7 @@ __device__ __forceinline__ void xc_half(double (&psi)[K], const double (&fd)[K],
         #pragma unroll
         for (int c = 0; c < NC; ++c) t[c] = t[c] - fd[PAR + 2 * c];
         #pragma unroll
-        for (int c = 0; c < NC; ++c) t[c] = t[c] * r.fac;
+        for (int c = 0; c < NC; ++c) t[c] = t[c] * fac;
     } else {
         const XcRow<1> &g = cr;
         #pragma unroll
@@ -149,7 +151,7 @@ __device__ __forceinline__ void xc_half(double (&psi)[K], const double (&fd)[K],
             temp = temp + g.C * ((Se - So) - (So - Sw));
             temp = temp + (g.D * (Snn - Sss) * a.ratio + g.E * (Se - Sw)) * a.delx / 2.0;
             temp = temp + (g.F * So - fd[m]) * a.delxSqr;
-            t[c] = temp * g.fac;
+            t[c] = temp * fac;
         }
     }
     #pragma unroll
@@ -279,6 +281,15 @@ xc_cluster_kernel(const XcArgs a)
                 g.F = rv[4 * a.rpitch + j]; g.fac = rv[5 * a.rpitch + j];
             }
         }
+        // Chebyshev (xinv_opts.accel): the factor of a half sweep is omega_h / den with the denominator of the row,
+        // formed as the reference forms it in every cell (numbas.py:364-367, :1151-1153; row-constant operands)
+        double den = 1.0;
+        if (a.accel) {
+            if constexpr (KIND == 0) den = (cr.An + cr.Ac) * a.ratioSqr + (cr.C + cr.C);
+            else                     den = (cr.A * a.ratioSqr + cr.C) * 2.0 - cr.F * a.delxSqr;
+        }
+        double om = a.st[b].omega, om_prev = om;     // omega of the next half sweep / before the sweep that may be undone
+        bool om_first = (a.st[b].sweeps_done == 0), om_first_prev = om_first;
         // ---- fill the tile: own rows (with the periodic ghosts), halo rows straight from HBM ----
         if (act) {
             #pragma unroll
@@ -304,6 +315,13 @@ xc_cluster_kernel(const XcArgs a)
         // had been tested right away (numbas.py:401-414: fields, flags and loop counts are unchanged by the lag).
         bool pending = false;
         for (int sweep = 0; sweep < a.nsweeps; ++sweep) {
+            double f0 = cr.fac, f1 = cr.fac;
+            if (a.accel) {
+                om_prev = om; om_first_prev = om_first;
+                const double w1 = xd_cheb_next(om, a.rho2, om_first);
+                f0 = om / den; f1 = w1 / den;
+                om = xd_cheb_next(w1, a.rho2, false); om_first = false;
+            }
             if (ctrl) {
                 if (post) {
                     if (halo_bytes) { xf_mbar_expect_tx(hb, halo_bytes); xf_mbar_expect_tx(hb + 1, halo_bytes); }
@@ -354,18 +372,18 @@ xc_cluster_kernel(const XcArgs a)
                 // ---- colour 0 ----
                 if (upd_row) {
                     if (par0 == 0)
-                        xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0]);
+                        xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0], f0);
                     else
-                        xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0]);
+                        xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[0], rS, rbS[0], f0);
                 }
                 xc_compute_sync(NW * 32);
                 if (edgeN || edgeS) xf_mbar_wait(hb, ph & 1u);
                 // ---- colour 1, and sum|psi| / count over psi != undef (numbas.py:1710-1728): thread -> warp -> a slot in every CTA ----
                 if (upd_row) {
                     if (par0 == 0)
-                        xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1]);
+                        xc_half<KIND, K, 1>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1], f1);
                     else
-                        xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1]);
+                        xc_half<KIND, K, 0>(psi, fd, cr, a, Tc, Tn, Ts, col0, westIdx, eastIdx, act, ghostE, ghostW, ghostEidx, rN, rbN[1], rS, rbS[1], f1);
                 }
                 double s0 = 0.0, s1 = 0.0;
                 int n = 0;
@@ -395,6 +413,7 @@ xc_cluster_kernel(const XcArgs a)
                     #pragma unroll
                     for (int m = 0; m < K; ++m) psi[m] = bkT[m * nth + tid];
                 }
+                om = om_prev; om_first = om_first_prev;
                 pending = false;
                 break;
             }
@@ -422,6 +441,7 @@ xc_cluster_kernel(const XcArgs a)
             for (int m = 0; m < K; ++m) if (m < nvalid) dst[m] = psi[m];
         }
         if (rank == 0 && post) {
+            st_.omega = om;
             a.st[b] = st_;
             if (!st_.active) atomicSub(a.nactive, 1);
         }
@@ -578,10 +598,11 @@ static inline int cluster_plan_build(ClusterPlan &cp, const FusedPlan &fp, int s
 }
 
 static inline int cluster_sweep(ClusterPlan &p, cudaStream_t stream, XdSliceState *st, int *nactive, double tol, i64 mxLoop,
-                                int zero_exit, int nsweeps, int64_t *launches)
+                                int zero_exit, int nsweeps, int accel, double rho2, int64_t *launches)
 {
     XcArgs &a = p.args;
     a.st = st; a.nactive = nactive; a.tol = tol; a.mxLoop = mxLoop; a.zero_exit = zero_exit; a.nsweeps = nsweeps;
+    a.accel = accel; a.rho2 = rho2;
     cudaError_t e = cudaSuccess;
 #define XC_GO(KD, K_) e = xc_launch<KD, K_>(p, stream, nullptr)
     XC_DISPATCH(p.kind, p.K, XC_GO);

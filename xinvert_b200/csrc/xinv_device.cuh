@@ -196,7 +196,17 @@ struct XdSliceState {
     int    nit;           // iterations the next pass runs on this slice (1..T)
     int    redo;          // next pass re-runs the final iteration(s); loop control already done
     int    pad_;
+    double omega;         // XINV_ACCEL_CHEBYSHEV: relaxation factor of the slice's next half sweep (resident / cluster engines)
 };
+
+// Chebyshev acceleration of SOR (xinv.h, xinv_opts.accel): the factor after `omega`; `first`: omega is omega_0 = 1.
+// One IEEE operation per step, the same on the host, on the device and in the test oracle.
+__host__ __device__ __forceinline__ double xd_cheb_next(double omega, double rho2, bool first)
+{
+    double t = first ? rho2 / 2.0 : (rho2 * omega) / 4.0;
+    t = 1.0 - t;
+    return 1.0 / t;
+}
 
 // Loop control of the reference after each sweep: numbas.py:401-414 (2-D
 // standard, with the norm==0 exit), :197-210 and :1186-1199 (no such exit).

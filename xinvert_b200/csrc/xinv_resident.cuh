@@ -40,6 +40,8 @@ struct XrArgs {
     i64 mxLoop;
     int zero_exit;
     int nsweeps;              // sweep budget of this launch
+    int accel;                // XINV_ACCEL_CHEBYSHEV: omega varies from half sweep to half sweep (xinv.h)
+    double rho2;
 };
 
 template <int KIND, bool HASB>
@@ -112,7 +114,11 @@ xr_resident_kernel(const XrArgs a)
 
         XdSliceState st_;
         if (tid == 0) st_ = a.st[b];
+        double om = a.st[b].omega;                   // Chebyshev: factor of the next half sweep (every thread keeps it)
+        bool om_first = (a.st[b].sweeps_done == 0);
         for (int sweep = 0; sweep < a.nsweeps; ++sweep) {
+            double w0 = a.q.optArg, w1 = a.q.optArg;
+            if (a.accel) { w0 = om; w1 = xd_cheb_next(om, a.rho2, om_first); om = xd_cheb_next(w1, a.rho2, false); om_first = false; }
             // ---- y-"extend" rows (numbas.py:284-310), as xd_extend_kernel ----
             if (g.bcy == XD_BC_EXTEND) {
                 for (i64 i = tid; i < nx; i += nth) {
@@ -126,6 +132,7 @@ xr_resident_kernel(const XrArgs a)
             }
             // ---- the colours, in place ----
             for (int colour = 0; colour < g.ncol; ++colour) {
+                const double wq = (colour < base / 2) ? w0 : w1;
                 const i64 cells = (colour >= base) ? rows : rows * half;
                 for (i64 idx = tid; idx < cells; idx += nth) {
                     i64 j, i;
@@ -146,10 +153,10 @@ xr_resident_kernel(const XrArgs a)
                     const i64 ip = (i == nx - 1) ? 0 : i + 1;
                     const i64 im = (i == 0) ? nx - 1 : i - 1;
                     if (KIND == XD_STD2D)
-                        xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2], a.q.optArg, undef);
+                        xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2], wq, undef);
                     else
                         xd_update_gen2d<HASB>(sS, cA, cB, c2, c3, c4, c5, c6, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2],
-                                              a.q.p[3], a.q.p[4], a.q.optArg, undef);
+                                              a.q.p[3], a.q.p[4], wq, undef);
                 }
                 __syncthreads();
             }
@@ -174,6 +181,7 @@ xr_resident_kernel(const XrArgs a)
         double *out = a.S + (i64)b * N;
         for (i64 p = tid; p < N; p += nth) out[p] = sS[p];
         if (tid == 0) {
+            st_.omega = om;
             a.st[b] = st_;
             if (!st_.active) atomicSub(a.nactive, 1);
         }
@@ -236,10 +244,11 @@ static inline int resident_plan_build(ResidentPlan &p, int sm_count, int kind, b
 }
 
 static inline int resident_sweep(ResidentPlan &p, cudaStream_t stream, XdSliceState *st, int *nactive, double tol, i64 mxLoop,
-                                 int zero_exit, int nsweeps, int64_t *launches)
+                                 int zero_exit, int nsweeps, int accel, double rho2, int64_t *launches)
 {
     XrArgs &a = p.args;
     a.st = st; a.nactive = nactive; a.tol = tol; a.mxLoop = mxLoop; a.zero_exit = zero_exit; a.nsweeps = nsweeps;
+    a.accel = accel; a.rho2 = rho2;
     if (p.kind == XD_STD2D) {
         if (p.hasB) xr_resident_kernel<XD_STD2D, true><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
         else        xr_resident_kernel<XD_STD2D, false><<<p.grid, XR_THREADS, p.smem, stream>>>(a);

@@ -16,6 +16,7 @@ objects exposing ``data_ptr()`` (device; used in place).  There is no CPU
 implementation behind these functions.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -157,8 +158,9 @@ def _sync_torch_stream(device_array):
 # two sets of staging buffers): while one chunk is being solved the next one is copied to the device and the
 # previous result is copied back.  Every slice still stops on its own test; results do not depend on the cut.
 # ---------------------------------------------------------------------------
-PIPE_MIN_CELLS = 8 << 20          # a chunk keeps at least this many cells (the fused kernels lose efficiency below)
+PIPE_MIN_CELLS = int(os.environ.get("XINV_PIPE_MIN_CELLS", 8 << 20))          # a chunk keeps at least this many cells (the fused kernels lose efficiency below)
 PIPE_STREAMS = 2
+PIPE_MAX_CHUNKS = int(os.environ.get("XINV_PIPE_MAX_CHUNKS", 2 * PIPE_STREAMS))
 
 
 def _plan(batch, cells_per_slice, devices, pipelined):
@@ -176,7 +178,7 @@ def _plan(batch, cells_per_slice, devices, pipelined):
             nchunk = max(1, min(n, (n * cells_per_slice) // PIPE_MIN_CELLS))
             if nchunk > 1:
                 nchunk = max(nchunk, PIPE_STREAMS)
-            nchunk = min(nchunk, 2 * PIPE_STREAMS)          # a few chunks are enough to hide the copies
+            nchunk = min(nchunk, PIPE_MAX_CHUNKS)           # a few chunks are enough to hide the copies
         nchunk = max(nchunk, -(-n // MAX_BATCH))
         for k in range(nchunk):
             clo, chi = shard_bounds(n, nchunk, k)
@@ -235,7 +237,8 @@ def _execute(call, batch, cells_per_slice, ctx, devices, host, _contexts=None):
     return stats
 
 
-def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, profile=False, S_dev=None, devices=None):
+def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, profile=False, S_dev=None, devices=None,
+         accel=None):
     L = _lib.load()
     fl = _flags_array(flags, ops.batch)
     fn = {"std2d": L.xinv_std2d, "gen2d": L.xinv_gen2d, "std3d": L.xinv_std3d}[kind]
@@ -248,7 +251,8 @@ def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, pro
 
     def call(c, lo, hi):
         opts = _lib.make_opts(ordering=ordering, mem_space=_lib.MEM_DEVICE if ops.device else _lib.MEM_HOST,
-                              engine=engine, check_every=check_every, coef_strides=ops.strides, profile=profile)
+                              engine=engine, check_every=check_every, coef_strides=ops.strides, profile=profile,
+                              accel=accel)
         off = lambda p, stride: C.c_void_p(p + 8 * lo * stride) if p is not None else None
         ptr_args = [off(ops.S_ptr, ops.N)] + [off(p, st) for p, st in zip(ops.ptrs, ops.strides)]
         rc = fn(c.handle, *ptr_args, *fn_args_tail(fl[lo:hi], hi - lo), C.byref(opts))
@@ -262,7 +266,8 @@ def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, pro
 
 def solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg,
                       undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
-                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False, devices=None):
+                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False, devices=None,
+                      accel=None):
     """Batched ``invert_standard_2D`` (numbas.py:215-416) over S[..., ny, nx], in place.
 
     ``devices``: GPUs to cut the batch over (one context and one thread per GPU, from this process).
@@ -273,12 +278,12 @@ def solve_standard_2D(S, A, B, C_, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, opt
     tail = lambda fl, nb: (nb, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
                            float(delxSqr), float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
                            C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
-    return _run("std2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices)
+    return _run("std2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices, accel=accel)
 
 
 def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_undef, BCy, BCx,
                            delxSqr, ratioQtr, ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0),
-                           mxLoop=5000, tolerance=1e-8, check_every=0, ctx=None, out=None, devices=None):
+                           mxLoop=5000, tolerance=1e-8, check_every=0, ctx=None, out=None, devices=None, accel=None):
     """Poisson-type front end (``xinv_std2d_rows``): the user's forcing ``F_user[..., ny, nx]`` (host
     numpy array or CUDA tensor; cells equal to ``user_undef`` -- any NaN when that is NaN -- are
     land), per-row coefficients ``A_rows[ny]``, ``C_rows[ny]`` and an optional per-row forcing scale;
@@ -325,7 +330,7 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
     stage_F = (not device) and not _lib.is_pinned(Fh)      # pageable forcing: through pinned buffers, chunk by chunk
 
     def call(c, lo, hi):
-        opts = _lib.make_opts(mem_space=_lib.MEM_DEVICE if device else _lib.MEM_HOST, check_every=check_every)
+        opts = _lib.make_opts(mem_space=_lib.MEM_DEVICE if device else _lib.MEM_HOST, check_every=check_every, accel=accel)
         off = lambda p: C.c_void_p(p.value + 8 * lo * ny * nx)
         Fc = off(F_ptr)
         if stage_F and hi > lo:
@@ -347,7 +352,7 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
 
 def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_undef, BCy, BCx, delx, delxSqr, ratio,
                           ratioQtr, ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
-                          tolerance=1e-8, check_every=0, ctx=None, devices=None):
+                          tolerance=1e-8, check_every=0, ctx=None, devices=None, accel=None):
     """General-form front end (``xinv_gen2d_rows``): the user's forcing ``G_user[..., ny, nx]`` (host
     numpy array), ``rows[5, ny]`` = A, C, D, E, F of every row, and the forcing transform (``g_mode`` 0:
     G = forcing; 1: G = ((-forcing) / g_p1) / g_p2); returns ``(S, flags[batch, 3], stats)`` with ``S``
@@ -367,7 +372,7 @@ def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_unde
     fl = _flags_array(flags, batch)
 
     def call(c, lo, hi):
-        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
+        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every, accel=accel)
         o = 8 * lo * ny * nx
         rc = L.xinv_gen2d_rows(c.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
                                C.c_void_p(Gh.ctypes.data + o), int(g_mode), float(g_p1), float(g_p2),
@@ -384,7 +389,7 @@ def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_unde
 
 def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, BCz, BCy, BCx, delxSqr, ratio2Sqr,
                            ratio1Sqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
-                           check_every=0, ctx=None, devices=None):
+                           check_every=0, ctx=None, devices=None, accel=None):
     """invert_omega front end (``xinv_std3d_rows``): the user's forcing ``F_user[..., nz, ny, nx]`` (host numpy
     array), ``rows[4, ny]`` (A; the factor of B = N2 * rows[1]; the divisor of C = N2 / rows[2]; the forcing
     scale) and ``N2`` (a float64 buffer read through four element strides: batch, level, row, column; 0 =
@@ -412,7 +417,7 @@ def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, 
         n2 = n2p
 
     def call(c, lo, hi):
-        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every)
+        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every, accel=accel)
         o = 8 * lo * N
         n2_off = 8 * lo * int(n2_strides[0])
         Fc = Fh.ctypes.data + o
@@ -435,7 +440,8 @@ def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, 
 
 def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ratioQtr,
                      ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
-                     tolerance=1e-8, ordering="colour", engine="auto", check_every=0, ctx=None, profile=False, devices=None):
+                     tolerance=1e-8, ordering="colour", engine="auto", check_every=0, ctx=None, profile=False, devices=None,
+                      accel=None):
     """Batched ``invert_general_2D`` (numbas.py:987-1201) over S[..., ny, nx], in place."""
     B = _zero_to_none(B)
     ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("D", D), ("E", E), ("F", F), ("G", G)], 2)
@@ -443,19 +449,20 @@ def solve_general_2D(S, A, B, C_, D, E, F, G, BCy, BCx, delx, delxSqr, ratio, ra
     tail = lambda fl, nb: (nb, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
                            float(delx), float(delxSqr), float(ratio), float(ratioQtr), float(ratioSqr),
                            float(optArg), float(undef), C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
-    return _run("gen2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices)
+    return _run("gen2d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices, accel=accel)
 
 
 def solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1Sqr, optArg,
                       undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
-                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False, devices=None):
+                      ordering="colour", engine="auto", check_every=0, ctx=None, profile=False, devices=None,
+                      accel=None):
     """Batched ``invert_standard_3D`` (numbas.py:15-212) over S[..., nz, ny, nx], in place."""
     ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("F", F)], 3)
     nz, ny, nx = ops.core
     tail = lambda fl, nb: (nb, nz, ny, nx, _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx],
                            float(delxSqr), float(ratio2Sqr), float(ratio1Sqr), float(optArg), float(undef),
                            C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
-    return _run("std3d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices)
+    return _run("std3d", ops, tail, flags, ordering, engine, check_every, ctx, profile, S_dev=S, devices=devices, accel=accel)
 
 
 # ---------------------------------------------------------------------------
