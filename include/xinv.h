@@ -251,7 +251,30 @@ typedef struct xinv_flow_desc {
     double s1, s2;            /* GRAD: +1 / -1                                                                    */
     double deg2m;             /* GM_LL                                                                            */
     xinv_flow_axis y, x;
-    const double *rows;       /* [nrows][ny]                                                                      */
+    const double *rows;       /* ---- The remaining SOR kernels of numbas.py, on the generic colour engine ---------------------
+ * Same conventions as above (batch axis first, S in/out, flags[batch][3], opts may be NULL; XINV_ORDER_COLOUR
+ * only).  Each mirrors the numba signature it replaces, minus the arguments that kernel never reads:
+ *   xinv_std2d_test  numbas.invert_standard_2D_test (numbas.py:421-424): nine-point stencil with two cross-term
+ *                    coefficients (B, C), D in the role of invert_standard_2D's C and a linear term E;
+ *   xinv_gen3d       numbas.invert_general_3D (numbas.py:746-749);  bcz accepted and ignored as BCz is there;
+ *   xinv_std1d       numbas.invert_standard_1D (numbas.py:633-635): batch series of nx points; bcx may be
+ *                    XINV_BC_EXTEND here (end points copy their neighbour before every sweep). */
+int xinv_std2d_test(xinv_ctx *ctx, double *S, const double *A, const double *B, const double *C,
+                    const double *D, const double *E, const double *F,
+                    int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                    double delxSqr, double ratioQtr, double ratioSqr, double optArg, double undef,
+                    double *flags, int64_t mxLoop, double tolerance, const xinv_opts *opts);
+int xinv_gen3d(xinv_ctx *ctx, double *S, const double *A, const double *B, const double *C,
+               const double *D, const double *E, const double *F, const double *G, const double *H,
+               int64_t batch, int64_t nz, int64_t ny, int64_t nx, int bcz, int bcy, int bcx,
+               double delx, double delxSqr, double ratio2, double ratio1, double ratio2Sqr, double ratio1Sqr,
+               double optArg, double undef, double *flags, int64_t mxLoop, double tolerance,
+               const xinv_opts *opts);
+int xinv_std1d(xinv_ctx *ctx, double *S, const double *A, const double *B, const double *F,
+               int64_t batch, int64_t nx, int bcx, double delxSqr, double optArg, double undef,
+               double *flags, int64_t mxLoop, double tolerance, const xinv_opts *opts);
+
+/* [nrows][ny]                                                                      */
 } xinv_flow_desc;
 int xinv_flow2d(xinv_ctx *ctx, double *out1, double *out2, const double *S,
                 int64_t batch, int64_t ny, int64_t nx, const xinv_flow_desc *desc, const xinv_opts *opts);

@@ -37,6 +37,12 @@ def lib():
         L.xo_invert_general_2D.restype = None
         L.xo_invert_standard_3D.argtypes = [dp] * 5 + [i64, i64, i64, ci, ci, ci] + [dbl] * 5 + [dp, i64, dbl, ci]
         L.xo_invert_standard_3D.restype = None
+        L.xo_invert_standard_2D_test.argtypes = [dp] * 7 + [i64, i64, ci, ci] + [dbl] * 5 + [dp, i64, dbl, ci]
+        L.xo_invert_standard_2D_test.restype = None
+        L.xo_invert_general_3D.argtypes = [dp] * 9 + [i64, i64, i64, ci, ci, ci] + [dbl] * 8 + [dp, i64, dbl, ci]
+        L.xo_invert_general_3D.restype = None
+        L.xo_invert_standard_1D.argtypes = [dp] * 4 + [i64, ci] + [dbl] * 3 + [dp, i64, dbl, ci]
+        L.xo_invert_standard_1D.restype = None
         L.xo_colour_sweep_std2d.argtypes = [dp] * 5 + [i64, i64, ci] + [dbl] * 5 + [ci]
         L.xo_colour_sweep_std2d.restype = None
         L.xo_colour_of.argtypes = [ci, ci, i64, i64, i64]
@@ -126,3 +132,36 @@ def abs_norm(S, undef):
     """numbas.absNorm2D/3D (numbas.py:1689-1728)."""
     S = np.ascontiguousarray(S, dtype=np.float64)
     return lib().xo_abs_norm(S.ctypes.data, S.size, undef)
+
+
+def invert_standard_2D_test(S, A, B, C_, D, E, F, yc, xc, dely, delx, BCy, BCx, delxSqr,
+                            ratioQtr, ratioSqr, optArg, undef, flags, mxLoop, tolerance, ordering="lexicographic"):
+    """numbas.invert_standard_2D_test (numbas.py:420-629)."""
+    sh = (yc, xc)
+    lib().xo_invert_standard_2D_test(
+        _p(S, sh), _p(A, sh), _p(B, sh), _p(C_, sh), _p(D, sh), _p(E, sh), _p(F, sh),
+        yc, xc, _BC[BCy], _BC[BCx], delxSqr, ratioQtr, ratioSqr, optArg, undef,
+        _p(flags, (3,)), int(mxLoop), float(tolerance), _ORD[ordering])
+    return S
+
+
+def invert_general_3D(S, A, B, C_, D, E, F, G, H, zc, yc, xc, delz, dely, delx, BCz, BCy, BCx, delxSqr,
+                      ratio2, ratio1, ratio2Sqr, ratio1Sqr, optArg, undef, flags, mxLoop, tolerance,
+                      ordering="lexicographic"):
+    """numbas.invert_general_3D (numbas.py:745-984)."""
+    sh = (zc, yc, xc)
+    lib().xo_invert_general_3D(
+        _p(S, sh), _p(A, sh), _p(B, sh), _p(C_, sh), _p(D, sh), _p(E, sh), _p(F, sh), _p(G, sh), _p(H, sh),
+        zc, yc, xc, _BC[BCz], _BC[BCy], _BC[BCx], float(delx), delxSqr, ratio2, ratio1, ratio2Sqr, ratio1Sqr,
+        optArg, undef, _p(flags, (3,)), int(mxLoop), float(tolerance), _ORD[ordering])
+    return S
+
+
+def invert_standard_1D(S, A, B, F, xc, delx, BCx, delxSqr, optArg, undef, flags, mxLoop, tolerance,
+                       ordering="lexicographic"):
+    """numbas.invert_standard_1D (numbas.py:632-742)."""
+    sh = (xc,)
+    lib().xo_invert_standard_1D(
+        _p(S, sh), _p(A, sh), _p(B, sh), _p(F, sh), xc, _BC[BCx], delxSqr, optArg, undef,
+        _p(flags, (3,)), int(mxLoop), float(tolerance), _ORD[ordering])
+    return S

@@ -114,3 +114,73 @@ def run_std3d(mod, c, bcy, bcx, mxLoop, tol, omega=None, **kw):
                            p["del2"], p["del1"], "fixed", bcy, bcx, p["del1Sqr"], p["ratio2Sqr"],
                            p["ratio1Sqr"], p["optArg"] if omega is None else omega, UNDEF, fl, mxLoop, tol, **kw)
     return S, fl
+
+
+# ---- the remaining kernels ---------------------------------------------------------------------------
+def random_std2dt(ny, nx, seed, land=0.1):
+    """invert_standard_2D_test (numbas.py:420-629): A, D positive, B, C cross terms, E a small linear term."""
+    rng = np.random.default_rng(seed)
+    shape = (ny, nx)
+    c = dict(A=1.0 + 0.3 * rng.random(shape), B=0.1 * rng.standard_normal(shape), C=0.1 * rng.standard_normal(shape),
+             D=1.0 + 0.3 * rng.random(shape), E=-1e-11 * rng.random(shape), F=1e-9 * rng.standard_normal(shape),
+             S0=rng.standard_normal(shape), p=params2d(ny, nx, 1.1e5, 0.9e5))
+    c["F"][rng.random(shape) < land] = UNDEF
+    c["B"][rng.random(shape) < 0.02] = UNDEF
+    return c
+
+
+def random_gen3d(nz, ny, nx, seed, land=0.1):
+    """invert_general_3D (numbas.py:745-984)."""
+    rng = np.random.default_rng(seed)
+    shape = (nz, ny, nx)
+    c = {k: -(1.0 + 0.3 * rng.random(shape)) for k in "ABC"}
+    for k in "DEF":
+        c[k] = 1e-6 * rng.standard_normal(shape)
+    c["G"] = 1e-12 * rng.random(shape)
+    c["H"] = 1e-9 * rng.standard_normal(shape)
+    c["H"][rng.random(shape) < land] = UNDEF
+    c["E"][rng.random(shape) < 0.02] = UNDEF
+    c["S0"] = rng.standard_normal(shape)
+    delz, dely, delx = 2500.0, 1.1e5, 0.9e5
+    c["p"] = dict(gc3=nz, gc2=ny, gc1=nx, del3=delz, del2=dely, del1=delx, del1Sqr=delx ** 2, ratio2=delx / delz * 1e-2,
+                  ratio1=delx / dely, ratio2Sqr=(delx / delz) ** 2 * 1e-3, ratio1Sqr=(delx / dely) ** 2, optArg=1.3)
+    return c
+
+
+def random_std1d(nx, seed, land=0.05, batch=None):
+    """invert_standard_1D (numbas.py:632-742)."""
+    rng = np.random.default_rng(seed)
+    shape = (nx,) if batch is None else (batch, nx)
+    c = dict(A=1.0 + 0.3 * rng.random(shape), B=-1e-11 * rng.random(shape), F=1e-9 * rng.standard_normal(shape),
+             S0=rng.standard_normal(shape), p=dict(gc1=nx, del1=0.9e5, del1Sqr=0.9e5 ** 2, optArg=1.5))
+    c["F"][rng.random(shape) < land] = UNDEF
+    return c
+
+
+def run_std2dt(mod, c, bcy, bcx, mxLoop, tol, omega=None, **kw):
+    p = c["p"]
+    S = c["S0"].copy()
+    fl = np.array([0.0, 1.0, 0.0])
+    mod.invert_standard_2D_test(S, c["A"], c["B"], c["C"], c["D"], c["E"], c["F"], p["gc2"], p["gc1"], p["del2"], p["del1"],
+                                bcy, bcx, p["del1Sqr"], p["ratioQtr"], p["ratioSqr"], p["optArg"] if omega is None else omega,
+                                UNDEF, fl, mxLoop, tol, **kw)
+    return S, fl
+
+
+def run_gen3d(mod, c, bcy, bcx, mxLoop, tol, omega=None, **kw):
+    p = c["p"]
+    S = c["S0"].copy()
+    fl = np.array([0.0, 1.0, 0.0])
+    mod.invert_general_3D(S, *[c[k] for k in "ABCDEFGH"], p["gc3"], p["gc2"], p["gc1"], p["del3"], p["del2"], p["del1"],
+                          "fixed", bcy, bcx, p["del1Sqr"], p["ratio2"], p["ratio1"], p["ratio2Sqr"], p["ratio1Sqr"],
+                          p["optArg"] if omega is None else omega, UNDEF, fl, mxLoop, tol, **kw)
+    return S, fl
+
+
+def run_std1d(mod, c, bcx, mxLoop, tol, omega=None, **kw):
+    p = c["p"]
+    S = c["S0"].copy()
+    fl = np.array([0.0, 1.0, 0.0])
+    mod.invert_standard_1D(S, c["A"], c["B"], c["F"], p["gc1"], p["del1"], bcx, p["del1Sqr"],
+                           p["optArg"] if omega is None else omega, UNDEF, fl, mxLoop, tol, **kw)
+    return S, fl

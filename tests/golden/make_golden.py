@@ -276,6 +276,29 @@ def main():
     for bcx in ("fixed", "periodic"):
         out["bridge_std3d_extend"][f"S_{bcx}"] = bridge_redblack_std3d_extend(ref, c, bcx, 5, 1.3)
 
+    # ---- SURVEY 8f #3 kernels, lexicographic: cases.run_* call the reference module directly (same signatures) ----
+    c = cases.random_std2dt(24, 36, seed=161)
+    out["std2dt"] = _pack(c)
+    for bcy, bcx in BCS:
+        S, fl = cases.run_std2dt(ref, c, bcy, bcx, 9, -1.0, omega=1.2)
+        out["std2dt"][f"S_{bcy}_{bcx}_9"] = S
+        out["std2dt"][f"fl_{bcy}_{bcx}_9"] = fl
+    c = cases.random_gen3d(6, 12, 16, seed=162)
+    out["gen3d"] = _pack(c)
+    for bcy, bcx in BCS:
+        S, fl = cases.run_gen3d(ref, c, bcy, bcx, 7, -1.0, omega=1.3)
+        out["gen3d"][f"S_{bcy}_{bcx}_7"] = S
+        out["gen3d"][f"fl_{bcy}_{bcx}_7"] = fl
+    c = cases.random_std1d(41, seed=163)
+    out["std1d"] = _pack(c)
+    for bcx in ("fixed", "extend", "periodic"):
+        S, fl = cases.run_std1d(ref, c, bcx, 25, -1.0, omega=1.5)
+        out["std1d"][f"S_{bcx}_25"] = S
+        out["std1d"][f"fl_{bcx}_25"] = fl
+    S, fl = cases.run_std1d(ref, c, "fixed", 5000, 1e-9, omega=1.5)
+    out["std1d"]["S_fixed_tol"] = S
+    out["std1d"]["fl_fixed_tol"] = fl
+
     only = set(sys.argv[1:])
     for tag, d in out.items():
         if only and tag not in only:

@@ -1,0 +1,106 @@
+"""GPU: the remaining SOR kernels of numbas.py -- invert_standard_2D_test, invert_general_3D,
+invert_standard_1D -- on the generic colour engine, through the C-ABI entries xinv_std2d_test / xinv_gen3d /
+xinv_std1d, against the ordering-matched C oracle (whose lexicographic order is pinned bit for bit to the unmodified
+numba kernels: tests/test_oracle_vs_reference.py, tests/golden/{std2dt,gen3d,std1d}.npz).
+
+Bar: fields BIT-EXACT, identical loop counts; flags[1] to 1e-6 relative."""
+import numpy as np
+import pytest
+
+import oracle
+import xinvert_b200 as xb
+from tests import cases
+from xinvert_b200 import solvers
+
+pytestmark = pytest.mark.gpu
+
+BCS = [("fixed", "fixed"), ("fixed", "periodic"), ("extend", "fixed"), ("extend", "periodic")]
+
+
+def _check_flags(f_gpu, f_ref):
+    assert f_gpu[0] == f_ref[0]
+    assert f_gpu[2] == f_ref[2]
+    assert np.isclose(f_gpu[1], f_ref[1], rtol=1e-6, atol=1e-13)
+
+
+@pytest.mark.parametrize("bcy,bcx", BCS)
+@pytest.mark.parametrize("shape", [(24, 36), (33, 47), (3, 3), (70, 131)])
+def test_std2d_test_colour_bit_exact(gpu_ctx, bcy, bcx, shape):
+    """Nine-point stencil, four colours (+ two wrap-fix colours for odd nx with periodic-x), west-column quirks."""
+    c = cases.random_std2dt(*shape, seed=shape[0] + shape[1])
+    for sweeps in (0, 1, 7):
+        S_o, f_o = cases.run_std2dt(oracle, c, bcy, bcx, sweeps, -1.0, omega=1.2, ordering="colour")
+        S_g, f_g = cases.run_std2dt(xb, c, bcy, bcx, sweeps, -1.0, omega=1.2)
+        assert gpu_ctx.stats()["engine"] == "colour" and gpu_ctx.stats()["ncolours"] == (6 if bcx == "periodic" and shape[1] % 2 else 4)
+        assert np.array_equal(S_g, S_o), f"max diff {np.abs(S_g - S_o).max()}"
+        _check_flags(f_g, f_o)
+
+
+@pytest.mark.parametrize("bcy,bcx", BCS)
+def test_gen3d_colour_bit_exact(gpu_ctx, bcy, bcx):
+    for shape in [(7, 13, 16), (6, 12, 15), (5, 40, 70)]:
+        c = cases.random_gen3d(*shape, seed=5)
+        c["H"][:, :, 0] = cases.UNDEF                    # periodic-x: the west column ignores H (numbas.py:869)
+        S_o, f_o = cases.run_gen3d(oracle, c, bcy, bcx, 6, -1.0, ordering="colour")
+        S_g, f_g = cases.run_gen3d(xb, c, bcy, bcx, 6, -1.0)
+        assert np.array_equal(S_g, S_o), f"max diff {np.abs(S_g - S_o).max()}"
+        _check_flags(f_g, f_o)
+
+
+@pytest.mark.parametrize("bcx", ["fixed", "extend", "periodic"])
+@pytest.mark.parametrize("nx", [3, 41, 64, 1001])
+def test_std1d_colour_bit_exact(gpu_ctx, bcx, nx):
+    c = cases.random_std1d(nx, seed=nx)
+    for sweeps in (0, 1, 30):
+        S_o, f_o = cases.run_std1d(oracle, c, bcx, sweeps, -1.0, ordering="colour")
+        S_g, f_g = cases.run_std1d(xb, c, bcx, sweeps, -1.0)
+        assert np.array_equal(S_g, S_o), f"max diff {np.abs(S_g - S_o).max()}"
+        _check_flags(f_g, f_o)
+
+
+def test_more_kernels_to_tolerance_and_batched(gpu_ctx):
+    """To tolerance (loop counts); a batch of 1-D series with per-series stop; shared (stride 0) coefficients."""
+    c = cases.random_std2dt(40, 56, seed=9)
+    S_o, f_o = cases.run_std2dt(oracle, c, "fixed", "fixed", 3000, 1e-9, omega=1.3, ordering="colour")
+    S_g, f_g = cases.run_std2dt(xb, c, "fixed", "fixed", 3000, 1e-9, omega=1.3)
+    assert f_o[2] > 20 and np.array_equal(S_g, S_o)
+    _check_flags(f_g, f_o)
+    c = cases.random_gen3d(8, 20, 24, seed=10)
+    S_o, f_o = cases.run_gen3d(oracle, c, "extend", "periodic", 3000, 1e-9, ordering="colour")
+    S_g, f_g = cases.run_gen3d(xb, c, "extend", "periodic", 3000, 1e-9)
+    assert f_o[2] > 20 and np.array_equal(S_g, S_o)
+    _check_flags(f_g, f_o)
+    B = 37
+    c = cases.random_std1d(200, seed=11, batch=B)
+    land = c["F"] == cases.UNDEF
+    c["F"] *= np.linspace(0.1, 30.0, B)[:, None] ** 3
+    c["F"][land] = cases.UNDEF
+    one = cases.random_std1d(200, seed=12)
+    S = c["S0"].copy()
+    fl, st = solvers.solve_standard_1D(S, one["A"], one["B"], c["F"], "fixed", c["p"]["del1Sqr"], 1.5, cases.UNDEF,
+                                       (0.0, 1.0, 0.0), 4000, 1e-7)
+    loops = set()
+    for b in range(0, B, 4):
+        cb = dict(one, F=c["F"][b], S0=c["S0"][b])
+        S_o, f_o = cases.run_std1d(oracle, cb, "fixed", 4000, 1e-7, ordering="colour")
+        assert np.array_equal(S[b], S_o)
+        _check_flags(fl[b], f_o)
+        loops.add(int(f_o[2]))
+    assert len(loops) > 3
+
+
+def test_more_kernels_refuse_lexicographic(gpu_ctx):
+    c = cases.random_std1d(41, seed=1)
+    p = c["p"]
+    with pytest.raises(xb.XinvError):
+        solvers._run  # noqa: B018  (the ndarray-level entries take the colour ordering only)
+        from xinvert_b200 import _lib
+        import ctypes as C
+        L = _lib.load()
+        S = c["S0"].copy()
+        fl = np.array([[0.0, 1.0, 0.0]])
+        opts = _lib.make_opts(ordering="lexicographic")
+        rc = L.xinv_std1d(gpu_ctx.handle, C.c_void_p(S.ctypes.data), C.c_void_p(c["A"].ctypes.data), C.c_void_p(c["B"].ctypes.data),
+                          C.c_void_p(c["F"].ctypes.data), 1, 41, 0, p["del1Sqr"], 1.5, cases.UNDEF, C.c_void_p(fl.ctypes.data),
+                          10, -1.0, C.byref(opts))
+        _lib.check(rc)

@@ -63,6 +63,31 @@ def test_std3d_matches_reference(ref, bcy, bcx):
         assert np.array_equal(f_o, f_r)
 
 
+@pytest.mark.parametrize("bcy,bcx", BCS)
+def test_new_kernels_match_reference(ref, bcy, bcx):
+    """invert_standard_2D_test, invert_general_3D (incl. the west-column condition that skips H,
+    numbas.py:869) and invert_standard_1D, lexicographic order, bit for bit."""
+    for shape, seed in [((31, 44), 31), ((17, 23), 32)]:
+        c = cases.random_std2dt(*shape, seed=seed)
+        S_r, f_r = cases.run_std2dt(ref, c, bcy, bcx, 11, -1.0, omega=1.2)
+        S_o, f_o = cases.run_std2dt(oracle, c, bcy, bcx, 11, -1.0, omega=1.2)
+        assert np.array_equal(S_o, S_r) and np.array_equal(f_o, f_r)
+    for shape, seed in [((6, 14, 19), 33), ((9, 11, 12), 34)]:
+        c = cases.random_gen3d(*shape, seed=seed)
+        c["H"][:, :, 0] = cases.UNDEF                      # periodic-x: the west column is updated all the same
+        S_r, f_r = cases.run_gen3d(ref, c, bcy, bcx, 8, -1.0, omega=1.3)
+        S_o, f_o = cases.run_gen3d(oracle, c, bcy, bcx, 8, -1.0, omega=1.3)
+        assert np.array_equal(S_o, S_r) and np.array_equal(f_o, f_r)
+    c = cases.random_std1d(57, seed=35)
+    for b in (bcy, bcx):
+        S_r, f_r = cases.run_std1d(ref, c, b, 30, -1.0)
+        S_o, f_o = cases.run_std1d(oracle, c, b, 30, -1.0)
+        assert np.array_equal(S_o, S_r) and np.array_equal(f_o, f_r)
+    S_r, f_r = cases.run_std1d(ref, c, "fixed", 5000, 1e-9)
+    S_o, f_o = cases.run_std1d(oracle, c, "fixed", 5000, 1e-9)
+    assert np.array_equal(S_o, S_r) and np.array_equal(f_o, f_r) and f_r[2] > 20
+
+
 def test_c1_known_answer(ref):
     """SURVEY.md 8c KAT (6): 360x180 lat-lon Poisson, fixed/periodic, omega 1.4,
     tol 1e-8: the reference stops at loop 2380 with max|psi| = 13182413.993245527;

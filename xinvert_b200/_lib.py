@@ -67,6 +67,9 @@ _STD2D_ROWS = [_vp] * 6 + [_dbl, _dbl, _i64, _i64, _i64, _int, _int] + [_dbl] * 
 _GEN2D_ROWS = [_vp] * 4 + [_int, _dbl, _dbl, _dbl, _dbl, _i64, _i64, _i64, _int, _int] + [_dbl] * 7 + [_vp, _i64, _dbl, _P(XinvOpts)]
 _STD3D_ROWS = [_vp] * 5 + [_i64, _vp, _dbl, _dbl, _i64, _i64, _i64, _i64, _int, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
 _STD3D = [_vp] * 6 + [_i64, _i64, _i64, _i64, _int, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
+_STD2DT = [_vp] * 8 + [_i64, _i64, _i64, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
+_GEN3D = [_vp] * 10 + [_i64, _i64, _i64, _i64, _int, _int, _int] + [_dbl] * 8 + [_vp, _i64, _dbl, _P(XinvOpts)]
+_STD1D = [_vp] * 5 + [_i64, _i64, _int] + [_dbl] * 3 + [_vp, _i64, _dbl, _P(XinvOpts)]
 SYMBOLS = [
     ("xinv_create", _int, [_P(_vp), _int]),
     ("xinv_create_on_stream", _int, [_P(_vp), _int, _vp]),
@@ -92,6 +95,9 @@ SYMBOLS = [
     ("xinv_std3d_rows", _int, _STD3D_ROWS),
     ("xinv_gen2d", _int, _GEN2D),
     ("xinv_std3d", _int, _STD3D),
+    ("xinv_std2d_test", _int, _STD2DT),
+    ("xinv_gen3d", _int, _GEN3D),
+    ("xinv_std1d", _int, _STD1D),
     ("xinv_std2d_begin", _int, _STD2D),
     ("xinv_gen2d_begin", _int, _GEN2D),
     ("xinv_std3d_begin", _int, _STD3D),

@@ -382,7 +382,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     pb.kind = a.kind;
     pb.batch = a.batch;
     pb.hasB = (a.b_index >= 0 && a.coef[a.b_index] != nullptr);
-    pb.zero_exit = (a.kind == XD_STD2D);
+    pb.zero_exit = (a.kind == XD_STD2D || a.kind == XD_STD2DT || a.kind == XD_STD1D);   // kernels with the norm == 0 exit (numbas.py:410, :621, :735)
     pb.userS = a.S;
     pb.userFlags = a.flags;
     pb.mem_space = o.mem_space;
@@ -397,7 +397,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     g.bcy = a.bcy; g.bcx = a.bcx;
     g.i0 = (a.bcx == XINV_BC_PERIODIC) ? 0 : 1;
     g.i1 = (a.bcx == XINV_BC_PERIODIC) ? (int)a.nx : (int)a.nx - 1;
-    g.scheme = (pb.hasB && a.kind != XD_STD3D) ? 4 : 2;
+    g.scheme = (a.kind == XD_STD2DT || (pb.hasB && (a.kind == XD_STD2D || a.kind == XD_GEN2D))) ? 4 : 2;
     g.wrapfix = (a.bcx == XINV_BC_PERIODIC) && (a.nx & 1);
     g.ncol = xd_num_colours(g.scheme, g.wrapfix);
     for (int m = 0; m < 6; ++m) pb.q.p[m] = a.p[m];
@@ -419,6 +419,8 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     if (a.batch == 0) { pb.open = true; pb.h_nactive = 0; return XINV_OK; }
 
     if (pb.ordering == XINV_ORDER_LEX) {
+        if (a.kind > XD_STD3D)
+            return set_err(XINV_E_UNSUPPORTED, "lexicographic ordering is offered for the three hot-path kernels only");
         if (pb.hasB && a.bcx == XINV_BC_PERIODIC)
             return set_err(XINV_E_UNSUPPORTED, "lexicographic ordering with a 9-point stencil and periodic-x "
                                                "serialises completely; not offered on the GPU");
@@ -665,7 +667,7 @@ template <int KIND>
 static void launch_colour(xinv_ctx *c, Problem &pb, int colour, dim3 grid, int nxblk)
 {
     XdSliceState *st = (XdSliceState *)c->state.p;
-    if (pb.hasB && KIND != XD_STD3D)
+    if (pb.hasB && (KIND == XD_STD2D || KIND == XD_GEN2D))
         xd_sweep_colour_kernel<KIND, true><<<grid, XD_SWEEP_THREADS, 0, c->stream>>>(pb.dS, pb.q, pb.g, colour, nxblk, st);
     else
         xd_sweep_colour_kernel<KIND, false><<<grid, XD_SWEEP_THREADS, 0, c->stream>>>(pb.dS, pb.q, pb.g, colour, nxblk, st);
@@ -698,7 +700,12 @@ static int sweep_colour_engine(xinv_ctx *c, Problem &pb)
 {
     const XdGeom &g = pb.g;
     XdSliceState *st = (XdSliceState *)c->state.p;
-    if (g.bcy == XINV_BC_EXTEND) {
+    if (pb.kind == XD_STD1D) {
+        if (g.bcx == XINV_BC_EXTEND) {
+            xd_extend1d_kernel<<<(unsigned)((pb.batch + 127) / 128), 128, 0, c->stream>>>(pb.dS, g.nx, (int)pb.batch, pb.q.undef, st);
+            c->stats.kernel_launches++;
+        }
+    } else if (g.bcy == XINV_BC_EXTEND) {
         const i64 levels = (g.nz > 1) ? g.nz - 2 : 1;
         if (levels > 0) {
             dim3 grid((unsigned)((g.nx + 127) / 128), (unsigned)levels, (unsigned)pb.batch);
@@ -706,7 +713,7 @@ static int sweep_colour_engine(xinv_ctx *c, Problem &pb)
             c->stats.kernel_launches++;
         }
     }
-    const i64 rows = (g.ny >= 3 ? g.ny - 2 : 0) * (pb.kind == XD_STD3D ? (g.nz >= 3 ? g.nz - 2 : 0) : 1);
+    const i64 rows = (pb.kind == XD_STD1D) ? 1 : (g.ny >= 3 ? g.ny - 2 : 0) * (XD_IS3D(pb.kind) ? (g.nz >= 3 ? g.nz - 2 : 0) : 1);
     const int base = (g.scheme == 4) ? 4 : 2;
     if (rows > 0 && g.i1 > g.i0) {
         prof_mark(c, pb);
@@ -721,7 +728,10 @@ static int sweep_colour_engine(xinv_ctx *c, Problem &pb)
             dim3 grid((unsigned)(rows * nxblk), (unsigned)pb.batch, 1);
             if (pb.kind == XD_STD2D) launch_colour<XD_STD2D>(c, pb, col, grid, nxblk);
             else if (pb.kind == XD_GEN2D) launch_colour<XD_GEN2D>(c, pb, col, grid, nxblk);
-            else launch_colour<XD_STD3D>(c, pb, col, grid, nxblk);
+            else if (pb.kind == XD_STD3D) launch_colour<XD_STD3D>(c, pb, col, grid, nxblk);
+            else if (pb.kind == XD_STD2DT) launch_colour<XD_STD2DT>(c, pb, col, grid, nxblk);
+            else if (pb.kind == XD_GEN3D) launch_colour<XD_GEN3D>(c, pb, col, grid, nxblk);
+            else launch_colour<XD_STD1D>(c, pb, col, grid, nxblk);
             c->stats.kernel_launches++;
         }
         prof_mark(c, pb);
@@ -1000,6 +1010,60 @@ extern "C" int xinv_std3d_begin(xinv_ctx *ctx, double *S, const double *A, const
     a.p[0] = delxSqr; a.p[1] = ratio2Sqr; a.p[2] = ratio1Sqr;
     a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
     return problem_begin(ctx, a);
+}
+
+// ---- the remaining kernels of numbas.py (colour engine) ----
+extern "C" int xinv_std2d_test(xinv_ctx *ctx, double *S, const double *A, const double *B, const double *C,
+                               const double *D, const double *E, const double *F,
+                               int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                               double delxSqr, double ratioQtr, double ratioSqr, double optArg, double undef,
+                               double *flags, int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    BeginArgs a{};
+    a.kind = XD_STD2DT; a.S = S;
+    a.coef[0] = A; a.coef[1] = B; a.coef[2] = C; a.coef[3] = D; a.coef[4] = E; a.coef[5] = F; a.ncoef = 6; a.b_index = -1;
+    a.batch = batch; a.nz = 1; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delxSqr; a.p[1] = ratioQtr; a.p[2] = ratioSqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    int rc = problem_begin(ctx, a);
+    if (rc) return rc;
+    return run_to_completion(ctx);
+}
+
+extern "C" int xinv_gen3d(xinv_ctx *ctx, double *S, const double *A, const double *B, const double *C,
+                          const double *D, const double *E, const double *F, const double *G, const double *H,
+                          int64_t batch, int64_t nz, int64_t ny, int64_t nx, int bcz, int bcy, int bcx,
+                          double delx, double delxSqr, double ratio2, double ratio1, double ratio2Sqr, double ratio1Sqr,
+                          double optArg, double undef, double *flags, int64_t mxLoop, double tolerance,
+                          const xinv_opts *opts)
+{
+    if (!valid_bc(bcz)) return set_err(XINV_E_ARG, "bad boundary condition code");
+    BeginArgs a{};
+    a.kind = XD_GEN3D; a.S = S;
+    a.coef[0] = A; a.coef[1] = B; a.coef[2] = C; a.coef[3] = D; a.coef[4] = E; a.coef[5] = F; a.coef[6] = G; a.coef[7] = H;
+    a.ncoef = 8; a.b_index = -1;
+    a.batch = batch; a.nz = nz; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delx; a.p[1] = delxSqr; a.p[2] = ratio2; a.p[3] = ratio1; a.p[4] = ratio2Sqr; a.p[5] = ratio1Sqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    int rc = problem_begin(ctx, a);
+    if (rc) return rc;
+    return run_to_completion(ctx);
+}
+
+extern "C" int xinv_std1d(xinv_ctx *ctx, double *S, const double *A, const double *B, const double *F,
+                          int64_t batch, int64_t nx, int bcx, double delxSqr, double optArg, double undef,
+                          double *flags, int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    if (nx < 3) return set_err(XINV_E_ARG, "nx < 3");
+    BeginArgs a{};
+    a.kind = XD_STD1D; a.S = S;
+    a.coef[0] = A; a.coef[1] = B; a.coef[2] = F; a.ncoef = 3; a.b_index = -1;
+    a.batch = batch; a.nz = 1; a.ny = 1; a.nx = nx; a.bcy = XINV_BC_FIXED; a.bcx = bcx;
+    a.p[0] = delxSqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    int rc = problem_begin(ctx, a);
+    if (rc) return rc;
+    return run_to_completion(ctx);
 }
 
 extern "C" int xinv_std3d_rows(xinv_ctx *ctx, double *S_out, const double *rows, const double *N2,

@@ -5,7 +5,8 @@
 #pragma once
 #include "xinv_device.cuh"
 
-enum XdKind { XD_STD2D = 0, XD_GEN2D = 1, XD_STD3D = 2 };
+enum XdKind { XD_STD2D = 0, XD_GEN2D = 1, XD_STD3D = 2, XD_STD2DT = 3, XD_GEN3D = 4, XD_STD1D = 5 };
+#define XD_IS3D(kind) ((kind) == XD_STD3D || (kind) == XD_GEN3D)
 
 #define XD_SWEEP_THREADS 128
 
@@ -36,6 +37,18 @@ __global__ void xd_extend_kernel(double *__restrict__ S, XdGeom g, double undef,
     }
 }
 
+// invert_standard_1D: the 'extend' condition is along x -- the end points take their neighbour's value before every
+// sweep (numbas.py:686-690).  One thread per series.
+__global__ void xd_extend1d_kernel(double *__restrict__ S, i64 nx, int batch, double undef, const XdSliceState *__restrict__ st)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch || !st[b].active) return;
+    double *P = S + (i64)b * nx;
+    const double a = P[1], z = P[nx - 2];
+    if (a != undef) P[0] = a;
+    if (z != undef) P[nx - 1] = z;
+}
+
 // One colour of one sweep, in place.  Thread t of a row handles the t-th cell
 // of that colour in the row.  blockIdx.x = row * nxblk + xblk, blockIdx.y = slice.
 template <int KIND, bool HASB>
@@ -48,8 +61,9 @@ xd_sweep_colour_kernel(double *__restrict__ Sall, XdCoef q, XdGeom g, int colour
     const i64 row = blockIdx.x / nxblk;
     const int xb = (int)(blockIdx.x - row * nxblk);
     i64 k = 0, j;
-    if (KIND == XD_STD3D) { k = 1 + row / (g.ny - 2); j = 1 + row % (g.ny - 2); }
-    else                  { j = 1 + row; }
+    if (XD_IS3D(KIND))         { k = 1 + row / (g.ny - 2); j = 1 + row % (g.ny - 2); }
+    else if (KIND == XD_STD1D) { j = 0; }
+    else                       { j = 1 + row; }
     const i64 jk = j + k;
     const int base = (g.scheme == 4) ? 4 : 2;
     i64 i;
@@ -77,10 +91,17 @@ xd_sweep_colour_kernel(double *__restrict__ Sall, XdCoef q, XdGeom g, int colour
                               q.c[5] + b * q.cs[5], q.c[6] + b * q.cs[6],
                               g.nx, j, i, ip, im, q.p[0], q.p[1], q.p[2], q.p[3], q.p[4],
                               q.optArg, q.undef);
-    } else {
+    } else if (KIND == XD_STD3D) {
         xd_update_std3d(S, q.c[0] + b * q.cs[0], q.c[1] + b * q.cs[1], q.c[2] + b * q.cs[2],
                         q.c[3] + b * q.cs[3], g.ny, g.nx, k, j, i, ip, im,
                         q.p[0], q.p[1], q.p[2], q.optArg, q.undef);
+    } else if (KIND == XD_STD2DT) {
+        xd_update_std2dt(S, q.c[0] + b * q.cs[0], q.c[1] + b * q.cs[1], q.c[2] + b * q.cs[2], q.c[3] + b * q.cs[3],
+                         q.c[4] + b * q.cs[4], q.c[5] + b * q.cs[5], g.nx, j, i, ip, im, q.p[0], q.p[1], q.p[2], q.optArg, q.undef);
+    } else if (KIND == XD_GEN3D) {
+        xd_update_gen3d(S, q, b, g.ny, g.nx, k, j, i, ip, im);
+    } else {
+        xd_update_std1d(S, q.c[0] + b * q.cs[0], q.c[1] + b * q.cs[1], q.c[2] + b * q.cs[2], i, ip, im, q.p[0], q.optArg, q.undef);
     }
 }
 

@@ -158,6 +158,76 @@ __device__ __forceinline__ void xd_update_std3d(double *__restrict__ S,
     S[c] = Sc + temp;
 }
 
+// ---- the remaining kernels of numbas.py on the same skeleton (colour engine) ----
+
+// invert_standard_2D_test (numbas.py:420-629; interior :560-583, west :525-553 with the B[j+1,1] / S[j-1,0] quirks of
+// :538-539, east :588-611).  c[] = {A,B,C,D,E,F}; p[] = {delxSqr, ratioQtr, ratioSqr}
+__device__ __forceinline__ void xd_update_std2dt(double *__restrict__ S,
+    const double *__restrict__ A, const double *__restrict__ B, const double *__restrict__ C,
+    const double *__restrict__ D, const double *__restrict__ E, const double *__restrict__ F,
+    i64 nx, i64 j, i64 i, i64 ip, i64 im,
+    double delxSqr, double ratioQtr, double ratioSqr, double optArg, double undef)
+{
+    const i64 c = j * nx + i, n = c + nx, s = c - nx;
+    const i64 e = j * nx + ip, w = j * nx + im;
+    const double Fc = F[c], An = A[n], Ac = A[c], Bn = B[n], Bs = B[s], Ce = C[e], Cw = C[w], De = D[e], Dc = D[c], Ec = E[c];
+    const bool cond = (Fc != undef) & (An != undef) & (Ac != undef) & (Bn != undef) & (Bs != undef) &
+                      (Ce != undef) & (Cw != undef) & (De != undef) & (Dc != undef) & (Ec != undef);
+    if (!cond) return;
+    const double Bq = (i == 0) ? B[n + 1] : Bn;
+    const double Sc = S[c], Sn = S[n], Ss = S[s], Se = S[e], Sw = S[w];
+    const double Sne = S[n - i + ip], Snw = S[n - i + im];
+    const double Sse = S[s - i + ip], Ssw = S[s - i + im];
+    const double Sse2 = (i == 0) ? Ss : Sse;
+    const double t1 = (An * (Sn - Sc) - Ac * (Sc - Ss)) * ratioSqr;
+    const double t2 = (Bq * (Sne - Snw) - Bs * (Sse2 - Ssw)) * ratioQtr;
+    const double t3 = (Ce * (Sne - Sse) - Cw * (Snw - Ssw)) * ratioQtr;
+    const double t4 = (De * (Se - Sc) - Dc * (Sc - Sw));
+    double temp = (((t1 + t2) + t3) + t4) + (Ec * Sc - Fc) * delxSqr;
+    temp = temp * (optArg / (((An + Ac) * ratioSqr + (De + Dc)) - Ec * delxSqr));
+    S[c] = Sc + temp;
+}
+
+// invert_general_3D (numbas.py:745-984; interior :905-935, west :868-900 -- its condition names G twice and never
+// tests H, :869 --, east :940-972).  c[] = {A..H}; p[] = {delx, delxSqr, ratio2, ratio1, ratio2Sqr, ratio1Sqr}
+__device__ __forceinline__ void xd_update_gen3d(double *__restrict__ S, const XdCoef &q, i64 b,
+    i64 ny, i64 nx, i64 k, i64 j, i64 i, i64 ip, i64 im)
+{
+    const i64 pl = ny * nx;
+    const i64 row = k * pl + j * nx;
+    const i64 c = row + i, e = row + ip, w = row + im;
+    const i64 n = c + nx, s = c - nx, u = c + pl, d = c - pl;
+    const double undef = q.undef;
+    const double Ac = q.c[0][b * q.cs[0] + c], Bc = q.c[1][b * q.cs[1] + c], Cc = q.c[2][b * q.cs[2] + c];
+    const double Dc = q.c[3][b * q.cs[3] + c], Ec = q.c[4][b * q.cs[4] + c], Fc = q.c[5][b * q.cs[5] + c];
+    const double Gc = q.c[6][b * q.cs[6] + c], Hc = q.c[7][b * q.cs[7] + c];
+    bool cond = (Gc != undef) & (Ac != undef) & (Bc != undef) & (Cc != undef) & (Dc != undef) & (Ec != undef) & (Fc != undef);
+    if (i != 0) cond = cond & (Hc != undef);
+    if (!cond) return;
+    const double delx = q.p[0], delxSqr = q.p[1], ratio2 = q.p[2], ratio1 = q.p[3], ratio2Sqr = q.p[4], ratio1Sqr = q.p[5];
+    const double Sc = S[c], Su = S[u], Sd = S[d], Sn = S[n], Ss = S[s], Se = S[e], Sw = S[w];
+    double temp = Ac * ((Su - Sc) - (Sc - Sd)) * ratio2Sqr;
+    temp = temp + Bc * ((Sn - Sc) - (Sc - Ss)) * ratio1Sqr;
+    temp = temp + Cc * ((Se - Sc) - (Sc - Sw));
+    temp = temp + ((Dc * (Su - Sd) * ratio2 + Ec * (Sn - Ss) * ratio1) + Fc * (Se - Sw)) * delx / 2.0;
+    temp = temp + (Gc * Sc - Hc) * delxSqr;
+    temp = temp * (q.optArg / (((Ac * ratio2Sqr + Bc * ratio1Sqr) + Cc) * 2.0 - Gc * delxSqr));
+    S[c] = Sc + temp;
+}
+
+// invert_standard_1D (numbas.py:632-742; interior :703-710, west :694-700, east :713-719).  c[] = {A,B,F}; p[] = {delxSqr}
+__device__ __forceinline__ void xd_update_std1d(double *__restrict__ S,
+    const double *__restrict__ A, const double *__restrict__ B, const double *__restrict__ F,
+    i64 i, i64 ip, i64 im, double delxSqr, double optArg, double undef)
+{
+    const double Fc = F[i], Ac = A[i], Ae = A[ip], Bc = B[i];
+    if (!((Fc != undef) & (Ac != undef) & (Ae != undef) & (Bc != undef))) return;
+    const double Sc = S[i];
+    double temp = (Ae * (S[ip] - Sc) - Ac * (Sc - S[im])) / delxSqr + (Bc * Sc - Fc);
+    temp = temp * (optArg / ((Ae + Ac) / delxSqr - Bc));
+    S[i] = Sc + temp;
+}
+
 // ---------------------------------------------------------------------------
 // Deterministic block reduction of (sum, count): fixed shuffle tree inside a
 // warp, fixed order across warps.  Result valid in thread 0.

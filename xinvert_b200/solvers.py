@@ -241,7 +241,8 @@ def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, pro
          accel=None):
     L = _lib.load()
     fl = _flags_array(flags, ops.batch)
-    fn = {"std2d": L.xinv_std2d, "gen2d": L.xinv_gen2d, "std3d": L.xinv_std3d}[kind]
+    fn = {"std2d": L.xinv_std2d, "gen2d": L.xinv_gen2d, "std3d": L.xinv_std3d, "std2dt": L.xinv_std2d_test,
+          "gen3d": L.xinv_gen3d, "std1d": L.xinv_std1d}[kind]
     if ops.device:
         if S_dev is not None:
             _sync_torch_stream(S_dev)
@@ -468,6 +469,38 @@ def solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1S
 # ---------------------------------------------------------------------------
 # cal_flow epilogue (xinv_flow2d)
 # ---------------------------------------------------------------------------
+# ---- the remaining kernels of numbas.py (generic colour engine) ----
+def solve_standard_2D_test(S, A, B, C_, D, E, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg, undef=_UNDEF,
+                           flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8, check_every=0, ctx=None, devices=None):
+    """Batched ``invert_standard_2D_test`` (numbas.py:420-629) over S[..., ny, nx], in place."""
+    ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("D", D), ("E", E), ("F", F)], 2)
+    ny, nx = ops.core
+    tail = lambda fl, nb: (nb, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delxSqr), float(ratioQtr), float(ratioSqr),
+                           float(optArg), float(undef), C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("std2dt", ops, tail, flags, "colour", "auto", check_every, ctx, False, S_dev=S, devices=devices)
+
+
+def solve_general_3D(S, A, B, C_, D, E, F, G, H, BCz, BCy, BCx, delx, delxSqr, ratio2, ratio1, ratio2Sqr, ratio1Sqr, optArg,
+                     undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8, check_every=0, ctx=None, devices=None):
+    """Batched ``invert_general_3D`` (numbas.py:745-984) over S[..., nz, ny, nx], in place."""
+    ops = _Operands(S, [(k, v) for k, v in zip("ABCDEFGH", (A, B, C_, D, E, F, G, H))], 3)
+    nz, ny, nx = ops.core
+    tail = lambda fl, nb: (nb, nz, ny, nx, _lib.BC_CODES[BCz], _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delx),
+                           float(delxSqr), float(ratio2), float(ratio1), float(ratio2Sqr), float(ratio1Sqr), float(optArg),
+                           float(undef), C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("gen3d", ops, tail, flags, "colour", "auto", check_every, ctx, False, S_dev=S, devices=devices)
+
+
+def solve_standard_1D(S, A, B, F, BCx, delxSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8,
+                      check_every=0, ctx=None, devices=None):
+    """Batched ``invert_standard_1D`` (numbas.py:632-742) over S[..., nx], in place."""
+    ops = _Operands(S, [("A", A), ("B", B), ("F", F)], 1)
+    (nx,) = ops.core
+    tail = lambda fl, nb: (nb, nx, _lib.BC_CODES[BCx], float(delxSqr), float(optArg), float(undef),
+                           C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("std1d", ops, tail, flags, "colour", "auto", check_every, ctx, False, S_dev=S, devices=devices)
+
+
 def axis_diff(coord, edge=None, fill=(0.0, 0.0)):
     """How ``numpy.gradient`` differentiates along an axis with these coordinate values -- decided here exactly as
     numpy decides it -- for an unpadded line (``edge=None``: DataArray.differentiate, one-sided ends) or for the line
@@ -573,5 +606,36 @@ def invert_standard_3D(S, A, B, C_, F, zc, yc, xc, delz, dely, delx, BCz, BCy, B
         raise ValueError(f"S.shape {tuple(S.shape)} != (zc, yc, xc) = {(zc, yc, xc)}")
     fl, _ = solve_standard_3D(S, A, B, C_, F, BCz, BCy, BCx, delxSqr, ratio2Sqr, ratio1Sqr, optArg,
                               undef, flags, mxLoop, tolerance, **kw)
+    _store_flags(flags, fl)
+    return S
+
+
+def invert_standard_2D_test(S, A, B, C_, D, E, F, yc, xc, dely, delx, BCy, BCx, delxSqr,
+                            ratioQtr, ratioSqr, optArg, undef, flags, mxLoop, tolerance, **kw):
+    """Same positional signature as ``numbas.invert_standard_2D_test`` (numbas.py:421-424)."""
+    if tuple(S.shape) != (yc, xc):
+        raise ValueError(f"S.shape {tuple(S.shape)} != (yc, xc) = {(yc, xc)}")
+    fl, _ = solve_standard_2D_test(S, A, B, C_, D, E, F, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg, undef, flags,
+                                   mxLoop, tolerance, **kw)
+    _store_flags(flags, fl)
+    return S
+
+
+def invert_general_3D(S, A, B, C_, D, E, F, G, H, zc, yc, xc, delz, dely, delx, BCz, BCy, BCx, delxSqr,
+                      ratio2, ratio1, ratio2Sqr, ratio1Sqr, optArg, undef, flags, mxLoop, tolerance, **kw):
+    """Same positional signature as ``numbas.invert_general_3D`` (numbas.py:746-749)."""
+    if tuple(S.shape) != (zc, yc, xc):
+        raise ValueError(f"S.shape {tuple(S.shape)} != (zc, yc, xc) = {(zc, yc, xc)}")
+    fl, _ = solve_general_3D(S, A, B, C_, D, E, F, G, H, BCz, BCy, BCx, delx, delxSqr, ratio2, ratio1, ratio2Sqr, ratio1Sqr,
+                             optArg, undef, flags, mxLoop, tolerance, **kw)
+    _store_flags(flags, fl)
+    return S
+
+
+def invert_standard_1D(S, A, B, F, xc, delx, BCx, delxSqr, optArg, undef, flags, mxLoop, tolerance, **kw):
+    """Same positional signature as ``numbas.invert_standard_1D`` (numbas.py:633-635)."""
+    if tuple(S.shape) != (xc,):
+        raise ValueError(f"S.shape {tuple(S.shape)} != (xc,) = {(xc,)}")
+    fl, _ = solve_standard_1D(S, A, B, F, BCx, delxSqr, optArg, undef, flags, mxLoop, tolerance, **kw)
     _store_flags(flags, fl)
     return S
