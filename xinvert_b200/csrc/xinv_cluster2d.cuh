@@ -199,7 +199,7 @@ xc_cluster_kernel(const XcArgs a)
     double *bkT = reinterpret_cast<double *>(slot + 2 * R * NW);           // [K][threads]: every cell's value before a speculative sweep
     uint64_t *hb = reinterpret_cast<uint64_t *>(bkT + (size_t)K * nth);   // [2] halo values of colour 0 / 1 have arrived
     uint64_t *nb = hb + 2;                                                 // [2] norm partials have arrived (by parity of the sweep)
-    int *verdict = reinterpret_cast<int *>(nb + 2);                        // [1] "the slice goes on", written by the control warp
+    int *verdict = reinterpret_cast<int *>(nb + 2);                        // [2] "the slice goes on" by parity of the judged sweep, written by the control warp
     if (tid == 0) {
         xf_mbar_init(hb, 1); xf_mbar_init(hb + 1, 1); xf_mbar_init(nb, 1); xf_mbar_init(nb + 1, 1);
         xf_fence_barrier_init();
@@ -325,11 +325,11 @@ xc_cluster_kernel(const XcArgs a)
             if (ctrl) {
                 if (post) {
                     if (halo_bytes) { xf_mbar_expect_tx(hb, halo_bytes); xf_mbar_expect_tx(hb + 1, halo_bytes); }
-                    xf_mbar_expect_tx(nb + (sp & 1u), norm_bytes);
+                    if (R > 1) xf_mbar_expect_tx(nb + (sp & 1u), norm_bytes);
                 }
                 if (pending) {                                     // the stop test of the previous sweep
                     const unsigned pp = sp - 1u;
-                    xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
+                    if (R > 1) xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
                     double ts = 0.0, tn = 0.0;
                     {
                         const double2 *sl = slot + (pp & 1u) * (R * NW);
@@ -341,7 +341,7 @@ xc_cluster_kernel(const XcArgs a)
                         tn += __shfl_xor_sync(0xffffffffu, tn, o);
                     }
                     xd_decide(st_, ts, (i64)tn, a.tol, a.mxLoop, a.zero_exit);   // the control warps of all CTAs, identically
-                    if (lane == 0) verdict[0] = st_.active;
+                    if (lane == 0) verdict[pp & 1u] = st_.active;   // two slots: the control warp is a sweep ahead of a slow reader
                 }
                 if (halo_bytes) xf_mbar_wait(hb, ph & 1u);         // (a barrier is armed again only after its phase is over)
             } else {
@@ -397,7 +397,9 @@ xc_cluster_kernel(const XcArgs a)
                 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sw_ += __shfl_xor_sync(0xffffffffu, sw_, o);
                 n = __reduce_add_sync(0xffffffffu, n);
-                if (lane < R)
+                if (R == 1) {                                      // a cluster of one CTA: plain stores, ordered by the CTA barrier below
+                    if (lane == 0) slot[(sp & 1u) * NW + warp] = make_double2(sw_, (double)n);
+                } else if (lane < R)
                     xc_st_async2(xc_mapa(xf_smem_u32(slot + (sp & 1u) * (R * NW) + rank * NW + warp), lane), sw_, (double)n,
                                  xc_mapa(xf_smem_u32(nb + (sp & 1u)), lane));
             }
@@ -405,10 +407,10 @@ xc_cluster_kernel(const XcArgs a)
             if (edgeN || edgeS || (ctrl && halo_bytes)) xf_mbar_wait(hb + 1, ph & 1u);
             ++ph;
             ++sp;
-            if (pending && !verdict[0]) {                          // the previous sweep was the last one: undo this one
+            if (pending && !verdict[sp & 1u]) {                    // (slot of sweep sp - 2) the previous sweep was the last one: undo this one
                 if (ctrl) {
                     const unsigned pp = sp - 1u;                   // its partials are on their way: let them land
-                    xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
+                    if (R > 1) xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
                 } else {
                     #pragma unroll
                     for (int m = 0; m < K; ++m) psi[m] = bkT[m * nth + tid];
@@ -421,7 +423,7 @@ xc_cluster_kernel(const XcArgs a)
         }
         if (pending && ctrl) {                                     // the sweep budget of this launch is used up: test the last sweep now
             const unsigned pp = sp - 1u;
-            xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
+            if (R > 1) xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
             double ts = 0.0, tn = 0.0;
             {
                 const double2 *sl = slot + (pp & 1u) * (R * NW);

@@ -66,8 +66,12 @@ xr_resident_kernel(const XrArgs a)
     const i64 nx = g.nx, ny = g.ny;
     const int base = (g.scheme == 4) ? 4 : 2;
     const i64 half = (nx + 1) / 2;
-    const i64 rows = (ny >= 3) ? ny - 2 : 0;
     const double undef = a.q.undef;
+    // thread layout of a colour step: W lanes per row, rpp rows at a time
+    int W = ((int)half + 7) & ~7;
+    if (W > nth) W = nth;
+    const int ty = tid / W, tx = tid - ty * W;
+    const int rpp = (nth / W) > 0 ? (nth / W) : 1;
 
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
         if (tid == 0) flag[0] = a.st[b].active;
@@ -130,33 +134,41 @@ xr_resident_kernel(const XrArgs a)
                 }
                 __syncthreads();
             }
-            // ---- the colours, in place ----
+            // ---- the colours, in place.  Threads are laid out as rows of W lanes (W = cells of one colour in a row,
+            //      rounded up to a multiple of 8): no division in the loop ----
             for (int colour = 0; colour < g.ncol; ++colour) {
                 const double wq = (colour < base / 2) ? w0 : w1;
-                const i64 cells = (colour >= base) ? rows : rows * half;
-                for (i64 idx = tid; idx < cells; idx += nth) {
-                    i64 j, i;
-                    if (colour >= base) {                      // wrap-fix colours: column nx-1 only
-                        j = 1 + idx; i = nx - 1;
-                    } else {
-                        const i64 r = idx / half, m = idx - r * half;
-                        j = 1 + r;
-                        if (g.scheme == 4) {
-                            if ((int)(j & 1) != (colour >> 1)) continue;
-                            i = 2 * m + (colour & 1);
-                        } else {
-                            i = 2 * m + ((j + colour) & 1);
-                        }
+                if (colour >= base) {                              // wrap-fix colours: column nx-1 only
+                    for (int j = 1 + tid; j < (int)ny - 1; j += nth) {
+                        const i64 i = nx - 1;
+                        if (i < g.i0 || i >= g.i1) continue;
+                        if (xd_colour(g.scheme, g.wrapfix, nx, j, j, i) != colour) continue;
+                        if (KIND == XD_STD2D)
+                            xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, 0, i - 1, a.q.p[0], a.q.p[1], a.q.p[2], wq, undef);
+                        else
+                            xd_update_gen2d<HASB>(sS, cA, cB, c2, c3, c4, c5, c6, nx, j, i, 0, i - 1, a.q.p[0], a.q.p[1], a.q.p[2],
+                                                  a.q.p[3], a.q.p[4], wq, undef);
                     }
-                    if (i < g.i0 || i >= g.i1) continue;
-                    if (xd_colour(g.scheme, g.wrapfix, nx, j, j, i) != colour) continue;
-                    const i64 ip = (i == nx - 1) ? 0 : i + 1;
-                    const i64 im = (i == 0) ? nx - 1 : i - 1;
-                    if (KIND == XD_STD2D)
-                        xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2], wq, undef);
-                    else
-                        xd_update_gen2d<HASB>(sS, cA, cB, c2, c3, c4, c5, c6, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2],
-                                              a.q.p[3], a.q.p[4], wq, undef);
+                } else {
+                    for (int j = 1 + ty; ty < rpp && j < (int)ny - 1; j += rpp) {     // (the last, partial row of threads idles)
+                        if (tx >= (int)half) continue;
+                        int i;
+                        if (g.scheme == 4) {
+                            if ((j & 1) != (colour >> 1)) continue;
+                            i = 2 * tx + (colour & 1);
+                        } else {
+                            i = 2 * tx + ((j + colour) & 1);
+                        }
+                        if (i < g.i0 || i >= g.i1) continue;
+                        if (xd_colour(g.scheme, g.wrapfix, nx, j, j, i) != colour) continue;
+                        const i64 ip = (i == (int)nx - 1) ? 0 : i + 1;
+                        const i64 im = (i == 0) ? nx - 1 : i - 1;
+                        if (KIND == XD_STD2D)
+                            xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2], wq, undef);
+                        else
+                            xd_update_gen2d<HASB>(sS, cA, cB, c2, c3, c4, c5, c6, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2],
+                                                  a.q.p[3], a.q.p[4], wq, undef);
+                    }
                 }
                 __syncthreads();
             }
