@@ -55,6 +55,9 @@ extern "C" {
 #define XINV_ENGINE_RESIDENT 3 /* small 2-D slices: the whole solve in one CTA, operands in shared memory */
 #define XINV_ENGINE_CLUSTER 4 /* 2-D, B==0, row coefficients: the whole solve in one thread-block cluster (psi in registers + DSMEM) */
 
+#define XINV_IO_F32_IN  1
+#define XINV_IO_F32_OUT 2
+
 #define XINV_ACCEL_NONE      0
 #define XINV_ACCEL_CHEBYSHEV 1
 
@@ -89,7 +92,12 @@ typedef struct xinv_opts {
      * radius that optArg is the optimal SOR factor of -- instead of using optArg from the first sweep on.  Colour
      * ordering only; runs on the cluster, resident and colour engines. */
     int32_t accel;            /* XINV_ACCEL_*                                            */
-    int32_t reserved_;
+    /* float32 I/O of the device front ends (xinv_std2d_rows / xinv_gen2d_rows / xinv_std3d_rows, host pointers only;
+     * SURVEY 8f #4 "float32 storage"): XINV_IO_F32_IN -- the user's forcing is float32 in host memory;
+     * XINV_IO_F32_OUT -- S_out is a float32 array.  Half the bytes cross PCIe; the values are widened / narrowed
+     * (round to nearest) on the device and the solve is the same float64 solve, so the result equals what promoting
+     * the forcing on the host and casting the result back gives (what xinvert_b200.apps does with float32 input). */
+    int32_t io_f32;
 } xinv_opts;
 
 /* Statistics of the last solve on a ctx. */

@@ -123,3 +123,33 @@ def test_float32_inputs_promotion_deviation(gpu_ctx):
     dev = np.abs(S.astype(np.float64) - Se).max() / scale
     print(f"float32 inputs: promoted-to-float64 solve vs float32-iterate emulation, max rel deviation {dev:.3e}")
     assert dev < 5e-5                                                 # ~300 sweeps of float32 round-off (eps = 6e-8)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_float32_io_of_the_poisson_front_end(gpu_ctx, pinned):
+    """xinv_opts.io_f32: a float32 forcing goes to the device as float32 and the result comes back as
+    float32 -- half the PCIe bytes -- widened / narrowed on the device around the same float64 solve: bit-equal to the
+    host-built path (which promotes on the host and casts the result back), land mask and batch included."""
+    import xinvert_b200 as xb
+    from tests.test_apps_host import _c1_zeta
+    ny, nx, T = 60, 120, 5
+    zeta, co = _c1_zeta(ny, nx)
+    rng = np.random.default_rng(4)
+    z = np.stack([zeta * (1 + 0.3 * t) + 1e-6 * rng.standard_normal((ny, nx)) for t in range(T)]).astype(np.float32)
+    lam, phi = np.deg2rad(co['lon'])[None, :], np.deg2rad(co['lat'])[:, None]
+    z[:, np.sin(5 * lam) * np.cos(3 * phi) > 0.6] = np.nan
+    if pinned:
+        zp = xb.pinned_empty(z.shape, np.float32)
+        zp[...] = z
+        z = zp
+    F = xb.DataArray(z, ['time', 'lat', 'lon'], dict(co, time=np.arange(T)))
+    ip = {'BCs': ['extend', 'periodic'], 'tolerance': 1e-8, 'mxLoop': 3000, 'printInfo': False}
+    ip1 = dict(ip)
+    s1 = xb.invert_Poisson(F, dims=['lat', 'lon'], iParams=ip1)                      # device front end, float32 I/O
+    st = ip1['stats']
+    assert s1.values.dtype == np.float32
+    assert st['h2d_bytes'] < 4 * z.size + 4096 and st['d2h_bytes'] == 4 * z.size     # float32 both ways (+ the row vectors)
+    s2 = xb.invert_Poisson(F, dims=['lat', 'lon'], iParams=dict(ip, engine='colour'))   # host-built path, promoted
+    assert s2.values.dtype == np.float32
+    assert np.array_equal(s1.values, s2.values, equal_nan=True)
+    assert np.isnan(s1.values).sum() == np.isnan(z).sum()

@@ -24,7 +24,7 @@ class XinvOpts(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("ordering", C.c_int32),
                 ("mem_space", C.c_int32), ("engine", C.c_int32),
                 ("check_every", C.c_int32), ("profile", C.c_int32),
-                ("coef_stride", C.c_int64 * 8), ("accel", C.c_int32), ("reserved_", C.c_int32)]
+                ("coef_stride", C.c_int64 * 8), ("accel", C.c_int32), ("io_f32", C.c_int32)]
 
 
 class XinvFlowAxis(C.Structure):
@@ -244,7 +244,7 @@ ACCEL_CODES = {None: 0, "none": 0, "chebyshev": 1}
 
 
 def make_opts(ordering="colour", mem_space=MEM_HOST, engine="auto", check_every=0,
-              coef_strides=None, profile=False, accel=None):
+              coef_strides=None, profile=False, accel=None, io_f32=0):
     o = XinvOpts()
     o.struct_size = C.sizeof(XinvOpts)
     o.ordering = ORDER_CODES[ordering]
@@ -253,6 +253,7 @@ def make_opts(ordering="colour", mem_space=MEM_HOST, engine="auto", check_every=
     o.check_every = int(check_every)
     o.profile = 1 if profile else 0
     o.accel = ACCEL_CODES[accel]
+    o.io_f32 = int(io_f32)
     for m in range(8):
         o.coef_stride[m] = -1
     if coef_strides:

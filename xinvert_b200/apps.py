@@ -471,7 +471,7 @@ def _poisson_device_front(F, dims, coords, icbc, mParams, iParams):
         return None
     mp = _update(default_mParams, mParams, ['g', 'Omega', 'Rearth'])
     g = _Grid(F, dims)
-    if not g.trailing or g.values.dtype != np.float64:
+    if not g.trailing or g.values.dtype not in (np.float64, np.float32):     # (float32: xinv_opts.io_f32)
         return None
     c = coords.lower()
     ny = g.core_shape[0]

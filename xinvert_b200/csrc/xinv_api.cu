@@ -86,6 +86,7 @@ struct Problem {
     ResidentPlan resident{};     // small 2-D slices (xinv_resident.cuh)
     ClusterPlan cluster{};       // small / medium 2-D slices with row coefficients, on top of `fused` (xinv_cluster2d.cuh)
     bool front = false;          // xinv_std2d_rows: S is output only, de-masked on the device
+    int io_f32 = 0;              // XINV_IO_F32_* (front ends, host pointers)
     int accel = 0;               // XINV_ACCEL_*
     double rho2 = 0.0;           // Chebyshev: squared Jacobi spectral radius implied by optArg
     double optArg0 = 0.0;        // the caller's optArg (q.optArg is overwritten per half sweep on the colour engine)
@@ -104,6 +105,7 @@ struct xinv_ctx {
     size_t prof_used = 0;
     // workspace (grown on demand, reused across calls)
     DevBuf stage[10];            // staged S, S2 and up to 8 coefficient arrays
+    DevBuf f32buf;               // float32 side of the front ends' I/O (xinv_opts.io_f32)
     DevBuf state, psum, pcnt, ticket, nactive, flags_in;
     XmWork xm_work;              // padded operand copies of the fused engine
     int *h_nactive_pinned = nullptr;
@@ -191,6 +193,7 @@ extern "C" void xinv_destroy(xinv_ctx *c)
     cudaStreamSynchronize(c->stream);
     xinv_nccl_finalize(c);
     for (auto &b : c->stage) release(b);
+    release(c->f32buf);
     release(c->state); release(c->psum); release(c->pcnt); release(c->ticket); release(c->nactive); release(c->flags_in);
     release(c->nccl_buf);
     fused_plan_release(c->pb.fused);
@@ -292,6 +295,18 @@ extern "C" int xinv_memcpy_d2h(xinv_ctx *c, void *dst, const void *src, int64_t 
     return XINV_OK;
 }
 
+// float32 I/O of the front ends (xinv_opts.io_f32): widen after the H2D copy, narrow before the D2H copy
+__global__ void xd_widen_kernel(double *__restrict__ dst, const float *__restrict__ src, i64 n)
+{
+    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) dst[p] = (double)src[p];
+}
+__global__ void xd_narrow_kernel(float *__restrict__ dst, const double *__restrict__ src, i64 n)
+{
+    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) dst[p] = __double2float_rn(src[p]);
+}
+
 // ---------------------------------------------------------------------------
 // begin: validate, stage, initialise per-slice state
 // ---------------------------------------------------------------------------
@@ -369,6 +384,9 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     if (o.ordering != XINV_ORDER_COLOUR && o.ordering != XINV_ORDER_LEX) return set_err(XINV_E_ARG, "bad ordering");
     if (o.mem_space != XINV_MEM_HOST && o.mem_space != XINV_MEM_DEVICE) return set_err(XINV_E_ARG, "bad mem_space");
     if (o.accel != XINV_ACCEL_NONE && o.accel != XINV_ACCEL_CHEBYSHEV) return set_err(XINV_E_ARG, "bad accel");
+    if (o.io_f32 & ~(XINV_IO_F32_IN | XINV_IO_F32_OUT)) return set_err(XINV_E_ARG, "bad io_f32");
+    if (o.io_f32 && (!a.front || o.mem_space != XINV_MEM_HOST))
+        return set_err(XINV_E_UNSUPPORTED, "io_f32 is offered by the device front ends (xinv_*_rows) with host pointers");
     if (o.accel && o.ordering != XINV_ORDER_COLOUR) return set_err(XINV_E_UNSUPPORTED, "accel needs the colour ordering");
     if (o.accel && (o.engine == XINV_ENGINE_FUSED)) return set_err(XINV_E_UNSUPPORTED, "accel runs on the cluster, resident and colour engines");
 
@@ -404,6 +422,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     pb.q.optArg = a.optArg;
     pb.q.undef = a.undef;
     pb.accel = o.accel;
+    pb.io_f32 = o.io_f32;
     pb.optArg0 = a.optArg;
     pb.omega = 1.0;
     pb.omega_first = true;
@@ -432,6 +451,21 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     XmFront front;
     X3Front front3;
     pb.front = a.front;
+    // the user's forcing -> device (float64, or float32 widened on the device)
+    auto stage_forcing = [&](void *dst, const void *src, size_t nelem) -> int {
+        if (!(o.io_f32 & XINV_IO_F32_IN)) {
+            CK(cudaMemcpyAsync(dst, src, nelem * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2d_bytes += (i64)(nelem * sizeof(double));
+            return XINV_OK;
+        }
+        int rc_ = ensure(c->f32buf, nelem * sizeof(float));
+        if (rc_) return rc_;
+        CK(cudaMemcpyAsync(c->f32buf.p, src, nelem * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (i64)(nelem * sizeof(float));
+        xd_widen_kernel<<<(unsigned)((nelem + 255) / 256), 256, 0, c->stream>>>((double *)dst, (const float *)c->f32buf.p, (i64)nelem);
+        c->stats.kernel_launches++;
+        return XINV_OK;
+    };
     if (a.front) {
         // the front end hands over A rows, C rows, the user's forcing and the row scale; S is output only
         if (o.ordering != XINV_ORDER_COLOUR || o.engine == XINV_ENGINE_COLOUR)
@@ -456,10 +490,10 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
                 if ((rc = ensure(c->stage[2 + 3], slice_bytes * a.batch))) return rc;       // user forcing
                 if ((rc = ensure(c->stage[2 + 0], 4 * row_bytes))) return rc;               // the four row vectors
                 if ((rc = ensure(c->stage[2 + 1], sizeof(double) * (size_t)a.n2_count))) return rc;   // N2
-                CK(cudaMemcpyAsync(c->stage[5].p, a.coef[3], slice_bytes * a.batch, cudaMemcpyHostToDevice, c->stream));
+                if ((rc = stage_forcing(c->stage[5].p, a.coef[3], (size_t)g.N * a.batch))) return rc;
                 CK(cudaMemcpyAsync(c->stage[2].p, a.coef[0], 4 * row_bytes, cudaMemcpyHostToDevice, c->stream));
                 CK(cudaMemcpyAsync(c->stage[3].p, a.coef[1], sizeof(double) * (size_t)a.n2_count, cudaMemcpyHostToDevice, c->stream));
-                c->stats.h2d_bytes += (i64)(slice_bytes * a.batch + 4 * row_bytes + sizeof(double) * (size_t)a.n2_count);
+                c->stats.h2d_bytes += (i64)(4 * row_bytes + sizeof(double) * (size_t)a.n2_count);
                 CK(cudaEventRecord(e1, c->stream));
                 CK(cudaStreamSynchronize(c->stream));
                 float ms = 0;
@@ -479,9 +513,9 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
             if (rc) return rc;
             if ((rc = ensure(c->stage[2 + 6], slice_bytes * a.batch))) return rc;   // user forcing
             if ((rc = ensure(c->stage[2 + 0], 5 * row_bytes))) return rc;           // A, C, D, E, F rows
-            CK(cudaMemcpyAsync(c->stage[8].p, a.coef[6], slice_bytes * a.batch, cudaMemcpyHostToDevice, c->stream));
+            if ((rc = stage_forcing(c->stage[8].p, a.coef[6], (size_t)g.N * a.batch))) return rc;
             CK(cudaMemcpyAsync(c->stage[2].p, a.coef[0], 5 * row_bytes, cudaMemcpyHostToDevice, c->stream));
-            c->stats.h2d_bytes += (i64)(slice_bytes * a.batch + 5 * row_bytes);
+            c->stats.h2d_bytes += (i64)(5 * row_bytes);
             CK(cudaEventRecord(e1, c->stream));
             CK(cudaStreamSynchronize(c->stream));
             float ms = 0;
@@ -500,11 +534,11 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
             if ((rc = ensure(c->stage[2 + 3], slice_bytes * a.batch))) return rc;   // user forcing
             if ((rc = ensure(c->stage[2 + 0], 3 * row_bytes))) return rc;           // A rows | C rows | scale
             double *rows = (double *)c->stage[2].p;
-            CK(cudaMemcpyAsync(c->stage[5].p, a.coef[3], slice_bytes * a.batch, cudaMemcpyHostToDevice, c->stream));
+            if ((rc = stage_forcing(c->stage[5].p, a.coef[3], (size_t)g.N * a.batch))) return rc;
             CK(cudaMemcpyAsync(rows, a.coef[0], row_bytes, cudaMemcpyHostToDevice, c->stream));
             CK(cudaMemcpyAsync(rows + a.ny, a.coef[2], row_bytes, cudaMemcpyHostToDevice, c->stream));
             if (a.f_scale) CK(cudaMemcpyAsync(rows + 2 * a.ny, a.f_scale, row_bytes, cudaMemcpyHostToDevice, c->stream));
-            c->stats.h2d_bytes += (i64)(slice_bytes * a.batch + (a.f_scale ? 3 : 2) * row_bytes);
+            c->stats.h2d_bytes += (i64)((a.f_scale ? 3 : 2) * row_bytes);
             CK(cudaEventRecord(e1, c->stream));
             CK(cudaStreamSynchronize(c->stream));
             float ms = 0;
@@ -859,7 +893,15 @@ extern "C" int xinv_end(xinv_ctx *c)
     }
     std::vector<XdSliceState> hs((size_t)pb.batch);
     CK(cudaEventRecord(c->ev0, c->stream));
-    if (pb.mem_space == XINV_MEM_HOST) {
+    if (pb.mem_space == XINV_MEM_HOST && (pb.io_f32 & XINV_IO_F32_OUT)) {
+        const i64 n = g.N * pb.batch;
+        int rc_ = ensure(c->f32buf, (size_t)n * sizeof(float));
+        if (rc_) return rc_;
+        xd_narrow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((float *)c->f32buf.p, pb.dS, n);
+        c->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(pb.userS, c->f32buf.p, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += (i64)sizeof(float) * n;
+    } else if (pb.mem_space == XINV_MEM_HOST) {
         CK(cudaMemcpyAsync(pb.userS, pb.dS, sizeof(double) * g.N * pb.batch, cudaMemcpyDeviceToHost, c->stream));
         c->stats.d2h_bytes += (i64)sizeof(double) * g.N * pb.batch;
     }

@@ -38,6 +38,13 @@
 
 namespace cg = cooperative_groups;
 
+// Norm partials of sweep n land in slot set n % XC_SLOTS of every CTA.  A CTA's control warp reads set n during its
+// sweep n+1; a CTA d hops away can run at most ~d/2 sweeps ahead of this CTA's compute warps (the halo exchange chains
+// them), which wait for the control warp at every sweep's CTA barrier -- so a set is rewritten (by sweep n + XC_SLOTS)
+// only if the control warp lagged its own compute warps by microseconds while holding no lock; four sets put that
+// beyond what a resident, non-preempted kernel can do (two would do in practice).
+#define XC_SLOTS 4u
+
 struct XcArgs {
     double *Sbuf[2];          // padded psi buffers of the fused plan [batch][ny][pitch]
     const double *Fd;         // [cbFd ? batch : 1][ny][pitch]
@@ -195,8 +202,8 @@ xc_cluster_kernel(const XcArgs a)
     const int ny = a.ny, nx = a.nx, TP = a.TP, NW = a.NW;
     const bool ctrl = (warp == NW);
     double *T = reinterpret_cast<double *>(xc_smem);                       // [(RPmax + 2)][TP]
-    double2 *slot = reinterpret_cast<double2 *>(T + (size_t)(a.RPmax + 2) * TP);   // [2][R * NW]: (sum, count) per compute warp of the cluster
-    double *bkT = reinterpret_cast<double *>(slot + 2 * R * NW);           // [K][threads]: every cell's value before a speculative sweep
+    double2 *slot = reinterpret_cast<double2 *>(T + (size_t)(a.RPmax + 2) * TP);   // [XC_SLOTS][R * NW]: (sum, count) per compute warp of the cluster
+    double *bkT = reinterpret_cast<double *>(slot + XC_SLOTS * R * NW);           // [K][threads]: every cell's value before a speculative sweep
     uint64_t *hb = reinterpret_cast<uint64_t *>(bkT + (size_t)K * nth);   // [2] halo values of colour 0 / 1 have arrived
     uint64_t *nb = hb + 2;                                                 // [2] norm partials have arrived (by parity of the sweep)
     int *verdict = reinterpret_cast<int *>(nb + 2);                        // [2] "the slice goes on" by parity of the judged sweep, written by the control warp
@@ -332,7 +339,7 @@ xc_cluster_kernel(const XcArgs a)
                     if (R > 1) xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
                     double ts = 0.0, tn = 0.0;
                     {
-                        const double2 *sl = slot + (pp & 1u) * (R * NW);
+                        const double2 *sl = slot + (pp % XC_SLOTS) * (R * NW);
                         for (int k = lane; k < R * NW; k += 32) { const double2 v = sl[k]; ts += v.x; tn += v.y; }
                     }
                     #pragma unroll
@@ -398,9 +405,9 @@ xc_cluster_kernel(const XcArgs a)
                 for (int o = 16; o > 0; o >>= 1) sw_ += __shfl_xor_sync(0xffffffffu, sw_, o);
                 n = __reduce_add_sync(0xffffffffu, n);
                 if (R == 1) {                                      // a cluster of one CTA: plain stores, ordered by the CTA barrier below
-                    if (lane == 0) slot[(sp & 1u) * NW + warp] = make_double2(sw_, (double)n);
+                    if (lane == 0) slot[(sp % XC_SLOTS) * NW + warp] = make_double2(sw_, (double)n);
                 } else if (lane < R)
-                    xc_st_async2(xc_mapa(xf_smem_u32(slot + (sp & 1u) * (R * NW) + rank * NW + warp), lane), sw_, (double)n,
+                    xc_st_async2(xc_mapa(xf_smem_u32(slot + (sp % XC_SLOTS) * (R * NW) + rank * NW + warp), lane), sw_, (double)n,
                                  xc_mapa(xf_smem_u32(nb + (sp & 1u)), lane));
             }
             __syncthreads();
@@ -426,7 +433,7 @@ xc_cluster_kernel(const XcArgs a)
             if (R > 1) xf_mbar_wait(nb + (pp & 1u), (pp >> 1) & 1u);
             double ts = 0.0, tn = 0.0;
             {
-                const double2 *sl = slot + (pp & 1u) * (R * NW);
+                const double2 *sl = slot + (pp % XC_SLOTS) * (R * NW);
                 for (int k = lane; k < R * NW; k += 32) { const double2 v = sl[k]; ts += v.x; tn += v.y; }
             }
             #pragma unroll
@@ -530,7 +537,7 @@ static inline bool xc_shape(ClusterPlan &cp, const XdGeom &g, int R, int K, int 
     if ((a.NW + 1) * 32 > max_threads || a.NW + 1 > 32) return false;       // + the control warp
     cp.K = K; cp.R = R;
     cp.threads = (a.NW + 1) * 32;
-    cp.smem = ((size_t)(a.RPmax + 2) * a.TP + (size_t)R * a.NW * 4 + (size_t)K * cp.threads) * sizeof(double) + 64;
+    cp.smem = ((size_t)(a.RPmax + 2) * a.TP + (size_t)R * a.NW * 8 + (size_t)K * cp.threads) * sizeof(double) + 64;
     return cp.smem <= 200 * 1024;
 }
 

@@ -309,12 +309,15 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
         F_ptr, S_ptr = ptr(F_user), ptr(S)
         keep = rows
     else:
-        Fh = _host_f64(F_user, "F")
+        # float32 forcing stays float32 on its way to the device and so does the result on its way back
+        # (xinv_opts.io_f32: half the PCIe bytes; widened / narrowed on the device, the solve is float64 either way)
+        f32 = isinstance(F_user, np.ndarray) and F_user.dtype == np.float32
+        Fh = np.ascontiguousarray(F_user) if f32 else _host_f64(F_user, "F")
         shape = Fh.shape
         # (page-locked and pooled: the device-to-host copy of the result runs at full PCIe rate)
-        S = out if out is not None else _lib.pinned_empty(shape)
-        if S.dtype != np.float64 or not S.flags["C_CONTIGUOUS"] or S.shape != shape:
-            raise ValueError("out must be a C-contiguous float64 array of the forcing's shape")
+        S = out if out is not None else _lib.pinned_empty(shape, Fh.dtype)
+        if S.dtype != Fh.dtype or not S.flags["C_CONTIGUOUS"] or S.shape != shape:
+            raise ValueError(f"out must be a C-contiguous {Fh.dtype} array of the forcing's shape")
         rows = [np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
                 for v in (A_rows, C_rows, F_row_scale)]
         ptr = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
@@ -329,13 +332,19 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
             raise ValueError(f"{name} must have shape ({ny},)")
     fl = _flags_array(flags, batch)
     stage_F = (not device) and not _lib.is_pinned(Fh)      # pageable forcing: through pinned buffers, chunk by chunk
+    io32 = 3 if (not device and Fh.dtype == np.float32) else 0
+    item = 4 if io32 else 8
+    if io32:
+        user_undef = float(np.float32(user_undef))         # the value the float32 cells actually hold
+        out_undef = float(np.float32(out_undef))
 
     def call(c, lo, hi):
-        opts = _lib.make_opts(mem_space=_lib.MEM_DEVICE if device else _lib.MEM_HOST, check_every=check_every, accel=accel)
-        off = lambda p: C.c_void_p(p.value + 8 * lo * ny * nx)
+        opts = _lib.make_opts(mem_space=_lib.MEM_DEVICE if device else _lib.MEM_HOST, check_every=check_every, accel=accel,
+                              io_f32=io32)
+        off = lambda p: C.c_void_p(p.value + item * lo * ny * nx)
         Fc = off(F_ptr)
         if stage_F and hi > lo:
-            buf = _lib.pinned_empty((hi - lo, ny, nx))      # pooled; filled by a few threads while the other chunk solves
+            buf = _lib.pinned_empty((hi - lo, ny, nx), Fh.dtype)      # pooled; filled by a few threads while the other chunk solves
             _lib.parallel_copy(buf, Fh.reshape(batch, ny, nx)[lo:hi])
             Fc = C.c_void_p(buf.ctypes.data)
         rc = L.xinv_std2d_rows(c.handle, off(S_ptr), ptr(rows[0]), ptr(rows[1]), Fc, ptr(rows[2]),
