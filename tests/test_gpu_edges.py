@@ -153,3 +153,44 @@ def test_float32_io_of_the_poisson_front_end(gpu_ctx, pinned):
     assert s2.values.dtype == np.float32
     assert np.array_equal(s1.values, s2.values, equal_nan=True)
     assert np.isnan(s1.values).sum() == np.isnan(z).sum()
+
+
+def test_float32_io_of_the_omega_and_gill_matsuno_front_ends(gpu_ctx, monkeypatch):
+    """The same for xinv_std3d_rows (invert_omega) and xinv_gen2d_rows (invert_GillMatsuno): float32 in, float32 out,
+    bit-equal to the host-built path on the promoted values."""
+    import xinvert_b200 as xb
+    from xinvert_b200 import apps
+    DA = xb.DataArray
+    nz, ny, nx, T = 9, 30, 64, 2
+    lev = 100000.0 - 10000.0 * np.arange(nz)
+    lat, lon = -58.0 + 4.0 * np.arange(ny), 5.625 * np.arange(nx)
+    rng = np.random.default_rng(5)
+    co = {'time': np.arange(T), 'LEV': lev, 'lat': lat, 'lon': lon}
+    Fv = (1e-17 * rng.standard_normal((T, nz, ny, nx))).astype(np.float32)
+    Fv[:, 2:5, 8:12, 10:20] = np.nan
+    F = DA(Fv, ['time', 'LEV', 'lat', 'lon'], co)
+    N2 = DA(1e-6 * (1 + 0.5 * rng.random(nz)), ['LEV'], {'LEV': lev})
+    ip = {'BCs': ['fixed', 'fixed', 'periodic'], 'tolerance': 1e-9, 'mxLoop': 40, 'printInfo': False}
+    kw = dict(dims=['LEV', 'lat', 'lon'], coords='lat-lon', mParams={'N2': N2})
+    ip_f = dict(ip)
+    w_f = xb.invert_omega(F, iParams=ip_f, **kw)
+    assert w_f.values.dtype == np.float32 and ip_f['stats']['d2h_bytes'] == 4 * Fv.size
+    with monkeypatch.context() as m:
+        m.setattr(apps, "_omega_device_front", lambda *a, **k: None)
+        w_h = xb.invert_omega(F, iParams=dict(ip), **kw)
+    assert w_h.values.dtype == np.float32
+    assert np.array_equal(w_f.values, w_h.values, equal_nan=True)
+    # Gill-Matsuno on a beta plane (general form)
+    ny, nx = 48, 96
+    y, x = np.linspace(-5e6, 5e6, ny), np.linspace(0, 4e7, nx, endpoint=False)
+    Q = (0.05 * np.exp(-((y[:, None] / 1e6) ** 2 + ((x[None, :] - 2e7) / 2e6) ** 2))).astype(np.float32)
+    Qd = DA(Q, ['y', 'x'], {'y': y, 'x': x})
+    ipg = {'BCs': ['fixed', 'periodic'], 'tolerance': 1e-9, 'mxLoop': 300, 'optArg': 1.4, 'printInfo': False}
+    kwg = dict(dims=['y', 'x'], coords='cartesian', mParams={'f0': 0.0, 'beta': 2e-11, 'epsilon': 1e-5, 'Phi': 5000.0})
+    ip_f = dict(ipg)
+    h_f = xb.invert_GillMatsuno(Qd, iParams=ip_f, **kwg)
+    assert h_f.values.dtype == np.float32 and ip_f['stats']['d2h_bytes'] == 4 * Q.size
+    with monkeypatch.context() as m:
+        m.setattr(apps, "_general_device_front", lambda *a, **k: None)
+        h_h = xb.invert_GillMatsuno(Qd, iParams=dict(ipg), **kwg)
+    assert np.array_equal(h_f.values, h_h.values, equal_nan=True)

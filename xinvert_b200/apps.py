@@ -622,7 +622,7 @@ def _general_device_front(rows_func, valid, F, dims, coords, icbc, mParams, iPar
         return None
     mp = _update(default_mParams, mParams, valid)
     g = _Grid(F, dims)
-    if not g.trailing or g.values.dtype != np.float64 or coords.lower() not in ('lat-lon', 'cartesian'):
+    if not g.trailing or g.values.dtype not in (np.float64, np.float32) or coords.lower() not in ('lat-lon', 'cartesian'):
         return None
     r = rows_func(g, coords, mp)
     ny = g.core_shape[0]
@@ -659,7 +659,7 @@ def _omega_device_front(F, dims, coords, icbc, mParams, iParams):
         return None
     mp = _update(default_mParams, mParams, ['f0', 'beta', 'N2', 'g', 'Omega', 'Rearth'])
     g = _Grid(F, dims)
-    if not g.trailing or g.values.dtype != np.float64:
+    if not g.trailing or g.values.dtype not in (np.float64, np.float32):
         return None
     c = coords.lower()
     nz, ny, nx = g.core_shape

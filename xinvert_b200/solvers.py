@@ -369,7 +369,11 @@ def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_unde
     solved from a zero initial guess and land set to ``out_undef`` (what apps.__mask_FS /
     __coeffs_GillMatsuno / __coeffs_Stommel / __template do on the host, on the device)."""
     L = _lib.load()
-    Gh = _host_f64(G_user, "G")
+    f32 = isinstance(G_user, np.ndarray) and G_user.dtype == np.float32      # xinv_opts.io_f32: float32 both ways
+    Gh = np.ascontiguousarray(G_user) if f32 else _host_f64(G_user, "G")
+    item, io32 = (4, 3) if f32 else (8, 0)
+    if f32:
+        user_undef, out_undef = float(np.float32(user_undef)), float(np.float32(out_undef))
     shape = Gh.shape
     if len(shape) < 2:
         raise ValueError("forcing needs at least 2 dimensions")
@@ -378,12 +382,12 @@ def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_unde
     rows = np.ascontiguousarray(rows, dtype=np.float64)
     if rows.shape != (5, ny):
         raise ValueError(f"rows must have shape (5, {ny})")
-    S = _lib.pinned_empty(shape)
+    S = _lib.pinned_empty(shape, Gh.dtype)
     fl = _flags_array(flags, batch)
 
     def call(c, lo, hi):
-        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every, accel=accel)
-        o = 8 * lo * ny * nx
+        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every, accel=accel, io_f32=io32)
+        o = item * lo * ny * nx
         rc = L.xinv_gen2d_rows(c.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
                                C.c_void_p(Gh.ctypes.data + o), int(g_mode), float(g_p1), float(g_p2),
                                float(user_undef), float(out_undef), hi - lo, ny, nx, _lib.BC_CODES[BCy],
@@ -406,7 +410,11 @@ def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, 
     broadcast).  Returns ``(S, flags[batch, 3], stats)``: solved from a zero initial guess, land = ``out_undef``
     (what apps.__mask_FS / __coeffs_omega / __template do on the host, on the device)."""
     L = _lib.load()
-    Fh = _host_f64(F_user, "F")
+    f32 = isinstance(F_user, np.ndarray) and F_user.dtype == np.float32      # xinv_opts.io_f32: float32 both ways
+    Fh = np.ascontiguousarray(F_user) if f32 else _host_f64(F_user, "F")
+    item, io32 = (4, 3) if f32 else (8, 0)
+    if f32:
+        user_undef, out_undef = float(np.float32(user_undef)), float(np.float32(out_undef))
     shape = Fh.shape
     if len(shape) < 3:
         raise ValueError("forcing needs at least 3 dimensions")
@@ -417,7 +425,7 @@ def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, 
         raise ValueError(f"rows must have shape (4, {ny})")
     n2 = np.ascontiguousarray(N2, dtype=np.float64).reshape(-1)
     st4 = (C.c_int64 * 4)(*[int(v) for v in n2_strides])
-    S = _lib.pinned_empty(shape)
+    S = _lib.pinned_empty(shape, Fh.dtype)
     fl = _flags_array(flags, batch)
     N = nz * ny * nx
     stage_F = not _lib.is_pinned(Fh)             # pageable operands: through pinned buffers (parallel copies)
@@ -427,12 +435,12 @@ def solve_standard_3D_rows(F_user, rows, N2, n2_strides, user_undef, out_undef, 
         n2 = n2p
 
     def call(c, lo, hi):
-        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every, accel=accel)
-        o = 8 * lo * N
+        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, check_every=check_every, accel=accel, io_f32=io32)
+        o = item * lo * N
         n2_off = 8 * lo * int(n2_strides[0])
         Fc = Fh.ctypes.data + o
         if stage_F and hi > lo:
-            buf = _lib.pinned_empty((hi - lo, nz, ny, nx))
+            buf = _lib.pinned_empty((hi - lo, nz, ny, nx), Fh.dtype)
             _lib.parallel_copy(buf, Fh.reshape(batch, nz, ny, nx)[lo:hi])
             Fc = buf.ctypes.data
         rc = L.xinv_std3d_rows(c.handle, C.c_void_p(S.ctypes.data + o), C.c_void_p(rows.ctypes.data),
