@@ -35,7 +35,7 @@ def _check(c, bcy, bcx, sweeps, tol=-1.0, omega=1.4, rc=None):
 
 
 VARIANTS = ["0", "1", "2", "3", "4"]          # general kernels (xinv_march2d.cuh: XM_VARIANTS)
-RC_VARIANTS = ["0", "1", "2", "3", "4", "5", "6"]  # RC kernels (XM_RC_VARIANTS; 2, 3, 5, 6 keep the records in shared memory; 6: T = 4)
+RC_VARIANTS = ["0", "1", "2", "3", "4", "5", "6", "7", "8"]  # RC kernels (XM_RC_VARIANTS; 2, 3, 5, 6, 7, 8 keep the records in shared memory; 6: T = 4; 7 (default), 8: 12 / 6 warps per CTA)
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
