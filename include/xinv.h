@@ -281,6 +281,17 @@ int xinv_gen3d(xinv_ctx *ctx, double *S, const double *A, const double *B, const
 int xinv_std1d(xinv_ctx *ctx, double *S, const double *A, const double *B, const double *F,
                int64_t batch, int64_t nx, int bcx, double delxSqr, double optArg, double undef,
                double *flags, int64_t mxLoop, double tolerance, const xinv_opts *opts);
+/*   xinv_bih2d       numbas.invert_general_bih_2D (numbas.py:1205-1210): 13-point biharmonic (invert_StommelMunk);
+ *                    nine colours (fifteen with periodic-x when nx is not a multiple of 3); rows 2 .. ny-3 and --
+ *                    unless x is periodic -- columns 2 .. nx-3 are updated; the two-row extend condition and the
+ *                    reference's edge-column arithmetic are reproduced as they are (xinv_device.cuh: xd_update_bih).
+ *                    The ten arrays are dense ([batch][ny][nx]; opts.coef_stride applies to the first eight). */
+int xinv_bih2d(xinv_ctx *ctx, double *S, const double *A, const double *B, const double *C, const double *D,
+               const double *E, const double *F, const double *G, const double *H, const double *I,
+               const double *J, int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+               double delxSSr, double delxTr, double delxSqr, double ratio, double ratioSSr, double ratioQtr,
+               double ratioSqr, double optArg, double undef, double *flags, int64_t mxLoop, double tolerance,
+               const xinv_opts *opts);
 
 /* [nrows][ny]                                                                      */
 } xinv_flow_desc;

@@ -43,6 +43,8 @@ def lib():
         L.xo_invert_general_3D.restype = None
         L.xo_invert_standard_1D.argtypes = [dp] * 4 + [i64, ci] + [dbl] * 3 + [dp, i64, dbl, ci]
         L.xo_invert_standard_1D.restype = None
+        L.xo_invert_general_bih_2D.argtypes = [dp] * 11 + [i64, i64, ci, ci] + [dbl] * 9 + [dp, i64, dbl, ci]
+        L.xo_invert_general_bih_2D.restype = None
         L.xo_colour_sweep_std2d.argtypes = [dp] * 5 + [i64, i64, ci] + [dbl] * 5 + [ci]
         L.xo_colour_sweep_std2d.restype = None
         L.xo_colour_of.argtypes = [ci, ci, i64, i64, i64]
@@ -163,5 +165,17 @@ def invert_standard_1D(S, A, B, F, xc, delx, BCx, delxSqr, optArg, undef, flags,
     sh = (xc,)
     lib().xo_invert_standard_1D(
         _p(S, sh), _p(A, sh), _p(B, sh), _p(F, sh), xc, _BC[BCx], delxSqr, optArg, undef,
+        _p(flags, (3,)), int(mxLoop), float(tolerance), _ORD[ordering])
+    return S
+
+
+def invert_general_bih_2D(S, A, B, C_, D, E, F, G, H, I, J, yc, xc, dely, delx, BCy, BCx, delxSSr, delxTr, delxSqr,
+                          ratio, ratioSSr, ratioQtr, ratioSqr, optArg, undef, flags, mxLoop, tolerance,
+                          ordering="lexicographic"):
+    """numbas.invert_general_bih_2D (numbas.py:1204-1586)."""
+    sh = (yc, xc)
+    lib().xo_invert_general_bih_2D(
+        _p(S, sh), *[_p(a, sh) for a in (A, B, C_, D, E, F, G, H, I, J)], yc, xc, _BC[BCy], _BC[BCx],
+        delxSSr, delxTr, delxSqr, ratio, ratioSSr, ratioQtr, ratioSqr, optArg, undef,
         _p(flags, (3,)), int(mxLoop), float(tolerance), _ORD[ordering])
     return S

@@ -184,3 +184,31 @@ def run_std1d(mod, c, bcx, mxLoop, tol, omega=None, **kw):
     mod.invert_standard_1D(S, c["A"], c["B"], c["F"], p["gc1"], p["del1"], bcx, p["del1Sqr"],
                            p["optArg"] if omega is None else omega, UNDEF, fl, mxLoop, tol, **kw)
     return S, fl
+
+
+def random_bih(ny, nx, seed, land=0.08):
+    """invert_general_bih_2D (numbas.py:1204-1586): A, C (4th-order terms) and B of one sign, the lower-order
+    coefficients small against them at these grid spacings."""
+    rng = np.random.default_rng(seed)
+    shape = (ny, nx)
+    dely, delx = 1.1e5, 0.9e5
+    c = dict(A=1.0 + 0.3 * rng.random(shape), B=2.0 + 0.3 * rng.random(shape), C=1.0 + 0.3 * rng.random(shape),
+             D=-1e-11 * rng.random(shape), E=1e-12 * rng.standard_normal(shape), F=-1e-11 * rng.random(shape),
+             G=1e-17 * rng.standard_normal(shape), H=1e-17 * rng.standard_normal(shape), I=1e-22 * rng.random(shape),
+             J=1e-19 * rng.standard_normal(shape), S0=rng.standard_normal(shape))
+    c["J"][rng.random(shape) < land] = UNDEF
+    c["E"][rng.random(shape) < 0.02] = UNDEF
+    ratio = delx / dely
+    c["p"] = dict(gc2=ny, gc1=nx, del2=dely, del1=delx, delxSSr=delx ** 4, delxTr=delx ** 3, del1Sqr=delx ** 2, ratio=ratio,
+                  ratioSSr=ratio ** 4, ratioQtr=ratio / 4.0, ratioSqr=ratio ** 2, optArg=1.2)
+    return c
+
+
+def run_bih(mod, c, bcy, bcx, mxLoop, tol, omega=None, **kw):
+    p = c["p"]
+    S = c["S0"].copy()
+    fl = np.array([0.0, 1.0, 0.0])
+    mod.invert_general_bih_2D(S, *[c[k] for k in "ABCDEFGHIJ"], p["gc2"], p["gc1"], p["del2"], p["del1"], bcy, bcx,
+                              p["delxSSr"], p["delxTr"], p["del1Sqr"], p["ratio"], p["ratioSSr"], p["ratioQtr"], p["ratioSqr"],
+                              p["optArg"] if omega is None else omega, UNDEF, fl, mxLoop, tol, **kw)
+    return S, fl

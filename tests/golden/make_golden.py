@@ -299,6 +299,13 @@ def main():
     out["std1d"]["S_fixed_tol"] = S
     out["std1d"]["fl_fixed_tol"] = fl
 
+    c = cases.random_bih(21, 27, seed=164)
+    out["bih2d"] = _pack(c)
+    for bcy, bcx in BCS:
+        S, fl = cases.run_bih(ref, c, bcy, bcx, 6, -1.0)
+        out["bih2d"][f"S_{bcy}_{bcx}_6"] = S
+        out["bih2d"][f"fl_{bcy}_{bcx}_6"] = fl
+
     only = set(sys.argv[1:])
     for tag, d in out.items():
         if only and tag not in only:

@@ -58,6 +58,23 @@ def test_std1d_colour_bit_exact(gpu_ctx, bcx, nx):
         _check_flags(f_g, f_o)
 
 
+@pytest.mark.parametrize("bcy,bcx", BCS)
+@pytest.mark.parametrize("shape", [(21, 27), (17, 23), (30, 33), (9, 8), (5, 5), (64, 130)])
+def test_biharmonic_colour_bit_exact(gpu_ctx, bcy, bcx, shape):
+    """invert_general_bih_2D: 13-point stencil, nine colours (fifteen with periodic-x and nx not a multiple of 3), the
+    two-row extend condition and the reference's edge-column arithmetic."""
+    if bcy == "extend" and bcx != "periodic" and shape[0] - 1 > shape[1]:
+        pytest.skip("the reference's second extend loop leaves the row here (undefined behaviour, see test_oracle_vs_reference._ub)")
+    c = cases.random_bih(*shape, seed=shape[0] * 7 + shape[1])
+    for sweeps in (0, 1, 6):
+        S_o, f_o = cases.run_bih(oracle, c, bcy, bcx, sweeps, -1.0, ordering="colour")
+        S_g, f_g = cases.run_bih(xb, c, bcy, bcx, sweeps, -1.0)
+        want = 15 if (bcx == "periodic" and shape[1] % 3) else 9
+        assert gpu_ctx.stats()["engine"] == "colour" and gpu_ctx.stats()["ncolours"] == want
+        assert np.array_equal(S_g, S_o), f"max diff {np.abs(S_g - S_o).max()} at {np.argwhere(S_g != S_o)[:5]}"
+        _check_flags(f_g, f_o)
+
+
 def test_more_kernels_to_tolerance_and_batched(gpu_ctx):
     """To tolerance (loop counts); a batch of 1-D series with per-series stop; shared (stride 0) coefficients."""
     c = cases.random_std2dt(40, 56, seed=9)
@@ -69,6 +86,11 @@ def test_more_kernels_to_tolerance_and_batched(gpu_ctx):
     S_o, f_o = cases.run_gen3d(oracle, c, "extend", "periodic", 3000, 1e-9, ordering="colour")
     S_g, f_g = cases.run_gen3d(xb, c, "extend", "periodic", 3000, 1e-9)
     assert f_o[2] > 20 and np.array_equal(S_g, S_o)
+    _check_flags(f_g, f_o)
+    c = cases.random_bih(40, 48, seed=12)
+    S_o, f_o = cases.run_bih(oracle, c, "fixed", "periodic", 400, 1e-7, ordering="colour")
+    S_g, f_g = cases.run_bih(xb, c, "fixed", "periodic", 400, 1e-7)
+    assert np.array_equal(S_g, S_o)
     _check_flags(f_g, f_o)
     B = 37
     c = cases.random_std1d(200, seed=11, batch=B)

@@ -88,6 +88,22 @@ def test_new_kernels_match_reference(ref, bcy, bcx):
     assert np.array_equal(S_o, S_r) and np.array_equal(f_o, f_r) and f_r[2] > 20
 
 
+@pytest.mark.parametrize("bcy,bcx", BCS)
+def test_biharmonic_matches_reference(ref, bcy, bcx):
+    """invert_general_bih_2D (numbas.py:1204-1586), lexicographic order, bit for bit -- including the two-row extend
+    condition, the edge columns' own operation order in the G term and the stale inner-loop index in the B term of the
+    two east columns (numbas.py:1495-1497, :1540-1542), for nx a multiple of 3 and not."""
+    for shape, seed in [((21, 27), 1), ((17, 23), 2), ((30, 33), 3), ((19, 12), 4), ((9, 8), 5)]:
+        if _ub(bcy, bcx, shape):
+            continue
+        c = cases.random_bih(*shape, seed=seed)
+        for sweeps in (0, 6):
+            S_r, f_r = cases.run_bih(ref, c, bcy, bcx, sweeps, -1.0)
+            S_o, f_o = cases.run_bih(oracle, c, bcy, bcx, sweeps, -1.0)
+            assert np.isfinite(S_r[S_r != cases.UNDEF]).all()
+            assert np.array_equal(S_o, S_r) and np.array_equal(f_o, f_r)
+
+
 def test_c1_known_answer(ref):
     """SURVEY.md 8c KAT (6): 360x180 lat-lon Poisson, fixed/periodic, omega 1.4,
     tol 1e-8: the reference stops at loop 2380 with max|psi| = 13182413.993245527;

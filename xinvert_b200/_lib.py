@@ -70,6 +70,7 @@ _STD3D = [_vp] * 6 + [_i64, _i64, _i64, _i64, _int, _int, _int] + [_dbl] * 5 + [
 _STD2DT = [_vp] * 8 + [_i64, _i64, _i64, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
 _GEN3D = [_vp] * 10 + [_i64, _i64, _i64, _i64, _int, _int, _int] + [_dbl] * 8 + [_vp, _i64, _dbl, _P(XinvOpts)]
 _STD1D = [_vp] * 5 + [_i64, _i64, _int] + [_dbl] * 3 + [_vp, _i64, _dbl, _P(XinvOpts)]
+_BIH2D = [_vp] * 12 + [_i64, _i64, _i64, _int, _int] + [_dbl] * 9 + [_vp, _i64, _dbl, _P(XinvOpts)]
 SYMBOLS = [
     ("xinv_create", _int, [_P(_vp), _int]),
     ("xinv_create_on_stream", _int, [_P(_vp), _int, _vp]),
@@ -98,6 +99,7 @@ SYMBOLS = [
     ("xinv_std2d_test", _int, _STD2DT),
     ("xinv_gen3d", _int, _GEN3D),
     ("xinv_std1d", _int, _STD1D),
+    ("xinv_bih2d", _int, _BIH2D),
     ("xinv_std2d_begin", _int, _STD2D),
     ("xinv_gen2d_begin", _int, _GEN2D),
     ("xinv_std3d_begin", _int, _STD3D),
@@ -257,7 +259,7 @@ def make_opts(ordering="colour", mem_space=MEM_HOST, engine="auto", check_every=
     for m in range(8):
         o.coef_stride[m] = -1
     if coef_strides:
-        for m, s in enumerate(coef_strides):
+        for m, s in enumerate(coef_strides[:8]):         # (arrays beyond the eighth are always dense: xinv_bih2d)
             o.coef_stride[m] = int(s)
     return o
 

@@ -104,7 +104,7 @@ struct xinv_ctx {
     std::vector<cudaEvent_t> prof_ev;   // pairs (begin, end) around the dominant kernels
     size_t prof_used = 0;
     // workspace (grown on demand, reused across calls)
-    DevBuf stage[10];            // staged S, S2 and up to 8 coefficient arrays
+    DevBuf stage[14];            // staged S, S2 and up to 12 coefficient arrays
     DevBuf f32buf;               // float32 side of the front ends' I/O (xinv_opts.io_f32)
     DevBuf state, psum, pcnt, ticket, nactive, flags_in;
     XmWork xm_work;              // padded operand copies of the fused engine
@@ -336,12 +336,12 @@ static int valid_bc(int bc) { return bc == XINV_BC_FIXED || bc == XINV_BC_EXTEND
 struct BeginArgs {
     int kind;
     double *S;
-    const double *coef[8];
+    const double *coef[12];
     int ncoef;
     int b_index;            // index of the optional B array in coef[] (or -1)
     i64 batch, nz, ny, nx;
     int bcy, bcx;
-    double p[6];
+    double p[8];
     double optArg, undef;
     double *flags;
     i64 mxLoop;
@@ -418,7 +418,14 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     g.scheme = (a.kind == XD_STD2DT || (pb.hasB && (a.kind == XD_STD2D || a.kind == XD_GEN2D))) ? 4 : 2;
     g.wrapfix = (a.bcx == XINV_BC_PERIODIC) && (a.nx & 1);
     g.ncol = xd_num_colours(g.scheme, g.wrapfix);
-    for (int m = 0; m < 6; ++m) pb.q.p[m] = a.p[m];
+    if (a.kind == XD_BIH2D) {                    // 13-point stencil: nine colours, columns 2 .. nx-3 unless periodic
+        g.scheme = 9;
+        g.wrapfix = (a.bcx == XINV_BC_PERIODIC) && (a.nx % 3 != 0);
+        g.ncol = g.wrapfix ? 15 : 9;
+        g.i0 = (a.bcx == XINV_BC_PERIODIC) ? 0 : 2;
+        g.i1 = (a.bcx == XINV_BC_PERIODIC) ? (int)a.nx : (int)a.nx - 2;
+    }
+    for (int m = 0; m < 8; ++m) pb.q.p[m] = a.p[m];
     pb.q.optArg = a.optArg;
     pb.q.undef = a.undef;
     pb.accel = o.accel;
@@ -551,7 +558,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
             pb.dS = a.S;
             front.F = a.coef[3]; front.Arow = a.coef[0]; front.Crow = a.coef[2]; front.scale = a.f_scale;
         }
-        for (int m = 0; m < 8; ++m) { pb.q.c[m] = nullptr; pb.q.cs[m] = 0; }
+        for (int m = 0; m < 12; ++m) { pb.q.c[m] = nullptr; pb.q.cs[m] = 0; }
     } else if (pb.mem_space == XINV_MEM_HOST) {
         CK(cudaEventRecord(e0, c->stream));
         int rc = ensure(c->stage[0], slice_bytes * a.batch);
@@ -561,7 +568,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
         c->stats.h2d_bytes += (i64)(slice_bytes * a.batch);
         for (int m = 0; m < a.ncoef; ++m) {
             if (!a.coef[m]) { pb.q.c[m] = nullptr; pb.q.cs[m] = 0; continue; }
-            const i64 stride = (o.coef_stride[m] < 0) ? g.N : o.coef_stride[m];
+            const i64 stride = (m >= 8 || o.coef_stride[m] < 0) ? g.N : o.coef_stride[m];      // (xinv_opts has eight strides)
             if (stride != 0 && stride != g.N) return set_err(XINV_E_ARG, "coef_stride[%d]=%lld must be -1, 0 or the slice size for host staging", m, stride);
             const size_t bytes = (stride == 0) ? slice_bytes : slice_bytes * a.batch;
             rc = ensure(c->stage[2 + m], bytes);
@@ -580,7 +587,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
         pb.dS = a.S;
         for (int m = 0; m < a.ncoef; ++m) {
             pb.q.c[m] = a.coef[m];
-            pb.q.cs[m] = (!a.coef[m]) ? 0 : ((o.coef_stride[m] < 0) ? g.N : o.coef_stride[m]);
+            pb.q.cs[m] = (!a.coef[m]) ? 0 : ((m >= 8 || o.coef_stride[m] < 0) ? g.N : o.coef_stride[m]);
         }
     }
 
@@ -734,6 +741,30 @@ static int sweep_colour_engine(xinv_ctx *c, Problem &pb)
 {
     const XdGeom &g = pb.g;
     XdSliceState *st = (XdSliceState *)c->state.p;
+    if (pb.kind == XD_BIH2D) {
+        if (g.bcy == XINV_BC_EXTEND) {
+            dim3 grid((unsigned)((g.nx + 127) / 128), (unsigned)pb.batch);
+            xd_extend_bih_kernel<<<grid, 128, 0, c->stream>>>(pb.dS, g, pb.q.undef, st);
+            c->stats.kernel_launches++;
+        }
+        const i64 rows4 = g.ny - 4;
+        if (rows4 > 0 && g.i1 > g.i0) {
+            prof_mark(c, pb);
+            for (int col = 0; col < g.ncol; ++col) {
+                const int nxblk = (col >= 9) ? 1 : (int)(((g.nx + 2) / 3 + XD_SWEEP_THREADS - 1) / XD_SWEEP_THREADS);
+                dim3 grid((unsigned)(rows4 * nxblk), (unsigned)pb.batch, 1);
+                xd_sweep_bih_kernel<<<grid, XD_SWEEP_THREADS, 0, c->stream>>>(pb.dS, pb.q, g, col, nxblk, st);
+                c->stats.kernel_launches++;
+            }
+            prof_mark(c, pb);
+        }
+        dim3 ngrid((unsigned)pb.nblk_norm, (unsigned)pb.batch, 1);
+        xd_norm_decide_kernel<<<ngrid, XD_NORM_THREADS, 0, c->stream>>>(
+            pb.dS, g.N, pb.q.undef, pb.nblk_norm, (double *)c->psum.p, (i64 *)c->pcnt.p,
+            (unsigned *)c->ticket.p, st, (int *)c->nactive.p, pb.tol, pb.mxLoop, pb.zero_exit);
+        c->stats.kernel_launches++;
+        return XINV_OK;
+    }
     if (pb.kind == XD_STD1D) {
         if (g.bcx == XINV_BC_EXTEND) {
             xd_extend1d_kernel<<<(unsigned)((pb.batch + 127) / 128), 128, 0, c->stream>>>(pb.dS, g.nx, (int)pb.batch, pb.q.undef, st);
@@ -1086,6 +1117,27 @@ extern "C" int xinv_gen3d(xinv_ctx *ctx, double *S, const double *A, const doubl
     a.ncoef = 8; a.b_index = -1;
     a.batch = batch; a.nz = nz; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
     a.p[0] = delx; a.p[1] = delxSqr; a.p[2] = ratio2; a.p[3] = ratio1; a.p[4] = ratio2Sqr; a.p[5] = ratio1Sqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    int rc = problem_begin(ctx, a);
+    if (rc) return rc;
+    return run_to_completion(ctx);
+}
+
+extern "C" int xinv_bih2d(xinv_ctx *ctx, double *S, const double *A, const double *B, const double *C, const double *D,
+                          const double *E, const double *F, const double *G, const double *H, const double *I,
+                          const double *J, int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                          double delxSSr, double delxTr, double delxSqr, double ratio, double ratioSSr, double ratioQtr,
+                          double ratioSqr, double optArg, double undef, double *flags, int64_t mxLoop, double tolerance,
+                          const xinv_opts *opts)
+{
+    if (ny < 5 || nx < 5) return set_err(XINV_E_ARG, "the 13-point stencil needs ny >= 5 and nx >= 5");
+    BeginArgs a{};
+    a.kind = XD_BIH2D; a.S = S;
+    const double *arr[10] = {A, B, C, D, E, F, G, H, I, J};
+    for (int m = 0; m < 10; ++m) a.coef[m] = arr[m];
+    a.ncoef = 10; a.b_index = -1;
+    a.batch = batch; a.nz = 1; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delxSSr; a.p[1] = delxTr; a.p[2] = delxSqr; a.p[3] = ratio; a.p[4] = ratioSSr; a.p[5] = ratioQtr; a.p[6] = ratioSqr;
     a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
     int rc = problem_begin(ctx, a);
     if (rc) return rc;

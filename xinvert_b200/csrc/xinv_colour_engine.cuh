@@ -1,11 +1,12 @@
 // xinv_colour_engine.cuh -- the generic "one in-place kernel per colour" engine.
-// Handles every stencil (5-, 7-, 9-point), every boundary condition and every
-// grid shape; the TMA-fused engine (xinv_fused2d.cuh) takes over for the hot
-// 2-D B==0 configurations.
+// Handles every stencil (5-, 7-, 9-point), every boundary condition, every grid shape and every
+// kernel of numbas.py offered here (XdKind); the marching engines (xinv_march2d.cuh, xinv_march3d.cuh),
+// the cluster engine (xinv_cluster2d.cuh) and the resident engine (xinv_resident.cuh) take over
+// wherever they apply ("Which engine runs").
 #pragma once
 #include "xinv_device.cuh"
 
-enum XdKind { XD_STD2D = 0, XD_GEN2D = 1, XD_STD3D = 2, XD_STD2DT = 3, XD_GEN3D = 4, XD_STD1D = 5 };
+enum XdKind { XD_STD2D = 0, XD_GEN2D = 1, XD_STD3D = 2, XD_STD2DT = 3, XD_GEN3D = 4, XD_STD1D = 5, XD_BIH2D = 6 };
 #define XD_IS3D(kind) ((kind) == XD_STD3D || (kind) == XD_GEN3D)
 
 #define XD_SWEEP_THREADS 128
@@ -47,6 +48,65 @@ __global__ void xd_extend1d_kernel(double *__restrict__ S, i64 nx, int batch, do
     const double a = P[1], z = P[nx - 2];
     if (a != undef) P[0] = a;
     if (z != undef) P[nx - 1] = z;
+}
+
+// invert_general_bih_2D: the two-row y-"extend" copy (numbas.py:1298-1343).  The periodic branch copies row 1 into row 0
+// BEFORE it refreshes row 1 from row 2; the non-periodic branch copies row 2 into both and sets the 2 x 2 corners from
+// the diagonal cell (2, 2) etc.  One thread per column, the corners by the threads of columns 0 and nx-1 AFTER the rows
+// (the reference's order: a corner assignment overrides what the row loop wrote to (0, 1), (1, 1), ...).
+__global__ void xd_extend_bih_kernel(double *__restrict__ S, XdGeom g, double undef, const XdSliceState *__restrict__ st)
+{
+    const int b = blockIdx.y;
+    if (!st[b].active) return;
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 nx = g.nx, ny = g.ny;
+    if (i >= nx) return;
+    double *P = S + (i64)b * g.N;
+    double *r0 = P, *r1 = P + nx, *r2 = P + 2 * nx, *m1 = P + (ny - 1) * nx, *m2 = P + (ny - 2) * nx, *m3 = P + (ny - 3) * nx;
+    if (g.bcx == XD_BC_PERIODIC) {
+        if (r2[i] != undef) { r0[i] = r1[i]; r1[i] = r2[i]; }
+        if (m3[i] != undef) { m1[i] = m3[i]; m2[i] = m3[i]; }
+        return;
+    }
+    // columns 0, 1, nx-2, nx-1 end up with the corner values where the corner source is valid, else with what the row
+    // loop gave them (columns 1 and nx-2) or untouched (columns 0 and nx-1)
+    const bool wcorner = (i <= 1), ecorner = (i >= nx - 2);
+    const i64 src = wcorner ? 2 : (ecorner ? nx - 3 : i);
+    const bool inloop = (i >= 1 && i <= nx - 2);
+    {
+        const double a = r2[i], ac = r2[src];
+        if (inloop && a != undef) { r0[i] = a; r1[i] = a; }
+        if ((wcorner || ecorner) && ac != undef) { r0[i] = ac; r1[i] = ac; }
+    }
+    {
+        const double z = m3[i], zc = m3[src];
+        if (inloop && z != undef) { m1[i] = z; m2[i] = z; }
+        if ((wcorner || ecorner) && zc != undef) { m1[i] = zc; m2[i] = zc; }
+    }
+}
+
+// One colour of one biharmonic sweep, in place: blockIdx.x = row * nxblk + xblk over the rows 2 .. ny-3, thread t of a
+// row handles column 3 t + (colour mod 3) (colours 0..8) or one of the last two columns (wrap-fix colours 9..14).
+__global__ void __launch_bounds__(XD_SWEEP_THREADS)
+xd_sweep_bih_kernel(double *__restrict__ Sall, XdCoef q, XdGeom g, int colour, int nxblk, const XdSliceState *__restrict__ st)
+{
+    const int b = blockIdx.y;
+    if (!st[b].active) return;
+    const i64 row = blockIdx.x / nxblk;
+    const int xb = (int)(blockIdx.x - row * nxblk);
+    const i64 j = 2 + row;
+    i64 i;
+    if (colour >= 9) {
+        if (xb != 0 || threadIdx.x != 0) return;
+        i = g.nx - 2 + (colour - 9) / 3;
+        if ((int)(j % 3) != (colour - 9) % 3) return;
+    } else {
+        if ((int)(j % 3) != colour / 3) return;
+        i = 3 * ((i64)xb * blockDim.x + threadIdx.x) + (colour % 3);
+    }
+    if (i < g.i0 || i >= g.i1) return;
+    if (xd_colour_bih(g.wrapfix, g.nx, j, i) != colour) return;
+    xd_update_bih(Sall + (i64)b * g.N, q, b, g.nx, j, i, g.bcx == XD_BC_PERIODIC);
 }
 
 // One colour of one sweep, in place.  Thread t of a row handles the t-th cell

@@ -53,9 +53,9 @@ struct XdGeom {
 };
 
 struct XdCoef {
-    const double *c[8];   // coefficient / forcing arrays in C-ABI argument order
-    i64 cs[8];            // batch stride of each (elements); 0 = shared by batch
-    double p[6];          // scalar parameters, meaning per problem kind
+    const double *c[12];  // coefficient / forcing arrays in C-ABI argument order
+    i64 cs[12];           // batch stride of each (elements); 0 = shared by batch
+    double p[8];          // scalar parameters, meaning per problem kind
     double optArg, undef;
 };
 
@@ -226,6 +226,54 @@ __device__ __forceinline__ void xd_update_std1d(double *__restrict__ S,
     double temp = (Ae * (S[ip] - Sc) - Ac * (Sc - S[im])) / delxSqr + (Bc * Sc - Fc);
     temp = temp * (optArg / ((Ae + Ac) / delxSqr - Bc));
     S[i] = Sc + temp;
+}
+
+// invert_general_bih_2D (numbas.py:1204-1586): 13-point biharmonic.  c[] = {A..J}; p[] = {delxSSr, delxTr, delxSqr, ratio,
+// ratioSSr, ratioQtr, ratioSqr}.  Nine colours 3*(j mod 3) + (i mod 3) (everything a cell reads lies within +-2 rows /
+// columns); periodic-x with nx not a multiple of 3: the last two columns move to six extra colours.
+__host__ __device__ __forceinline__ int xd_colour_bih(int wrapfix, i64 nx, i64 j, i64 i)
+{
+    if (wrapfix && i >= nx - 2) return 9 + 3 * (int)(i - (nx - 2)) + (int)(j % 3);
+    return 3 * (int)(j % 3) + (int)(i % 3);
+}
+__device__ __forceinline__ i64 xd_wrapcol(i64 i, i64 nx) { i %= nx; return i < 0 ? i + nx : i; }
+// Interior numbas.py:1438-1479; periodic edge columns :1348-1390 (0), :1392-1434 (1), :1481-1524 (nx-2), :1526-1569 (nx-1),
+// with their quirks: the G term's operation order, and -- in the two east columns -- the B term's "two columns west"
+// operand taken at the stale inner-loop index (columns nx-7 / nx-6, negative indices wrapping) instead of nx-4 / nx-3.
+__device__ __forceinline__ void xd_update_bih(double *__restrict__ S, const XdCoef &q, i64 b, i64 nx, i64 j, i64 i, bool periodic)
+{
+    const i64 c = j * nx + i;
+    double v[10];
+    bool cond = true;
+    #pragma unroll
+    for (int m = 0; m < 10; ++m) { v[m] = q.c[m][b * q.cs[m] + c]; cond = cond & (v[m] != q.undef); }
+    if (!cond) return;
+    const double A = v[0], B = v[1], C = v[2], D = v[3], E = v[4], F = v[5], G = v[6], H = v[7], I = v[8], J = v[9];
+    const double delxSSr = q.p[0], delxTr = q.p[1], delxSqr = q.p[2], ratio = q.p[3], ratioSSr = q.p[4], ratioQtr = q.p[5],
+                 ratioSqr = q.p[6];
+    const bool edge = periodic && (i < 2 || i >= nx - 2);
+    i64 e1 = i + 1, e2 = i + 2, w1 = i - 1, w2 = i - 2, w2b = i - 2;
+    if (periodic) {
+        e1 = xd_wrapcol(e1, nx); e2 = xd_wrapcol(e2, nx); w1 = xd_wrapcol(w1, nx); w2 = xd_wrapcol(w2, nx); w2b = w2;
+        if (i == nx - 2) w2b = xd_wrapcol(nx - 7, nx);
+        if (i == nx - 1) w2b = xd_wrapcol(nx - 6, nx);
+    }
+    double *r0 = S + j * nx;
+    const double *rp1 = r0 + nx, *rp2 = r0 + 2 * nx, *rm1 = r0 - nx, *rm2 = r0 - 2 * nx;
+    const double Sc = r0[i];
+    double temp = A * ((((rp2[i] - 4.0 * rp1[i]) + 6.0 * Sc) - 4.0 * rm1[i]) + rm2[i]) * ratioSSr;
+    temp = temp + B * ((((((((rp2[e2] - 2.0 * rp2[i]) + rp2[w2b]) + -2.0 * r0[e2]) + 4.0 * Sc) - 2.0 * r0[w2b]) + rm2[e2]) -
+                        2.0 * rm2[i]) + rm2[w2b]) * ratioSqr / 16.0;
+    temp = temp + C * ((((r0[e2] - 4.0 * r0[e1]) + 6.0 * Sc) - 4.0 * r0[w1]) + r0[w2]);
+    temp = temp + D * ((rp1[i] - Sc) - (Sc - rm1[i])) * ratioSqr * delxSqr;
+    temp = temp + E * ((rp1[e1] - rm1[e1]) - (rp1[w1] - rm1[w1])) * ratioQtr * delxSqr;
+    temp = temp + F * ((r0[e1] - Sc) - (Sc - r0[w1])) * delxSqr;
+    if (edge) temp = temp + G * (rp1[i] - rm1[i]) * delxTr / 2.0 * ratio;
+    else      temp = temp + G * (rp1[i] - rm1[i]) * delxTr * ratio / 2.0;
+    temp = temp + H * (r0[e1] - r0[w1]) * delxTr / 2.0;
+    temp = temp + (I * Sc - J) * delxSSr;
+    temp = temp * (-q.optArg / ((((A * ratioSSr + C) * 6.0 + B * ratioSqr / 4.0) - (D * ratioSqr + F) * 2.0 * delxSqr) + I * delxSSr));
+    r0[i] = Sc + temp;
 }
 
 // ---------------------------------------------------------------------------

@@ -150,15 +150,12 @@ xr_resident_kernel(const XrArgs a)
                                                   a.q.p[3], a.q.p[4], wq, undef);
                     }
                 } else {
-                    for (int j = 1 + ty; ty < rpp && j < (int)ny - 1; j += rpp) {     // (the last, partial row of threads idles)
+                    // 4-colour scheme: only the rows of this colour's parity (every second row) are visited
+                    const int jstep = (g.scheme == 4) ? 2 : 1;
+                    const int jfirst = (g.scheme == 4) ? (((colour >> 1) & 1) ? 1 : 2) : 1;
+                    for (int j = jfirst + jstep * ty; ty < rpp && j < (int)ny - 1; j += jstep * rpp) {     // (the last, partial row of threads idles)
                         if (tx >= (int)half) continue;
-                        int i;
-                        if (g.scheme == 4) {
-                            if ((j & 1) != (colour >> 1)) continue;
-                            i = 2 * tx + (colour & 1);
-                        } else {
-                            i = 2 * tx + ((j + colour) & 1);
-                        }
+                        const int i = (g.scheme == 4) ? 2 * tx + (colour & 1) : 2 * tx + ((j + colour) & 1);
                         if (i < g.i0 || i >= g.i1) continue;
                         if (xd_colour(g.scheme, g.wrapfix, nx, j, j, i) != colour) continue;
                         const i64 ip = (i == (int)nx - 1) ? 0 : i + 1;

@@ -242,7 +242,7 @@ def _run(kind, ops, fn_args_tail, flags, ordering, engine, check_every, ctx, pro
     L = _lib.load()
     fl = _flags_array(flags, ops.batch)
     fn = {"std2d": L.xinv_std2d, "gen2d": L.xinv_gen2d, "std3d": L.xinv_std3d, "std2dt": L.xinv_std2d_test,
-          "gen3d": L.xinv_gen3d, "std1d": L.xinv_std1d}[kind]
+          "gen3d": L.xinv_gen3d, "std1d": L.xinv_std1d, "bih2d": L.xinv_bih2d}[kind]
     if ops.device:
         if S_dev is not None:
             _sync_torch_stream(S_dev)
@@ -518,6 +518,20 @@ def solve_standard_1D(S, A, B, F, BCx, delxSqr, optArg, undef=_UNDEF, flags=(0.0
     return _run("std1d", ops, tail, flags, "colour", "auto", check_every, ctx, False, S_dev=S, devices=devices)
 
 
+def solve_general_bih_2D(S, A, B, C_, D, E, F, G, H, I, J, BCy, BCx, delxSSr, delxTr, delxSqr, ratio, ratioSSr, ratioQtr,
+                         ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8, check_every=0,
+                         ctx=None, devices=None):
+    """Batched ``invert_general_bih_2D`` (numbas.py:1204-1586) over S[..., ny, nx], in place."""
+    ops = _Operands(S, [(k, v) for k, v in zip("ABCDEFGHIJ", (A, B, C_, D, E, F, G, H, I, J))], 2)
+    if any(st == 0 for st in ops.strides[8:]):
+        raise ValueError("I and J must have S's shape (one slice per batch entry)")
+    ny, nx = ops.core
+    tail = lambda fl, nb: (nb, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delxSSr), float(delxTr), float(delxSqr),
+                           float(ratio), float(ratioSSr), float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
+                           C.c_void_p(fl.ctypes.data), int(mxLoop), float(tolerance))
+    return _run("bih2d", ops, tail, flags, "colour", "auto", check_every, ctx, False, S_dev=S, devices=devices)
+
+
 def axis_diff(coord, edge=None, fill=(0.0, 0.0)):
     """How ``numpy.gradient`` differentiates along an axis with these coordinate values -- decided here exactly as
     numpy decides it -- for an unpadded line (``edge=None``: DataArray.differentiate, one-sided ends) or for the line
@@ -654,5 +668,16 @@ def invert_standard_1D(S, A, B, F, xc, delx, BCx, delxSqr, optArg, undef, flags,
     if tuple(S.shape) != (xc,):
         raise ValueError(f"S.shape {tuple(S.shape)} != (xc,) = {(xc,)}")
     fl, _ = solve_standard_1D(S, A, B, F, BCx, delxSqr, optArg, undef, flags, mxLoop, tolerance, **kw)
+    _store_flags(flags, fl)
+    return S
+
+
+def invert_general_bih_2D(S, A, B, C_, D, E, F, G, H, I, J, yc, xc, dely, delx, BCy, BCx, delxSSr, delxTr, delxSqr,
+                          ratio, ratioSSr, ratioQtr, ratioSqr, optArg, undef, flags, mxLoop, tolerance, **kw):
+    """Same positional signature as ``numbas.invert_general_bih_2D`` (numbas.py:1205-1210)."""
+    if tuple(S.shape) != (yc, xc):
+        raise ValueError(f"S.shape {tuple(S.shape)} != (yc, xc) = {(yc, xc)}")
+    fl, _ = solve_general_bih_2D(S, A, B, C_, D, E, F, G, H, I, J, BCy, BCx, delxSSr, delxTr, delxSqr, ratio, ratioSSr,
+                                 ratioQtr, ratioSqr, optArg, undef, flags, mxLoop, tolerance, **kw)
     _store_flags(flags, fl)
     return S
