@@ -259,7 +259,18 @@ typedef struct xinv_flow_desc {
     double s1, s2;            /* GRAD: +1 / -1                                                                    */
     double deg2m;             /* GM_LL                                                                            */
     xinv_flow_axis y, x;
-    const double *rows;       /* ---- The remaining SOR kernels of numbas.py, on the generic colour engine ---------------------
+    const double *rows;       /* Dense front end (invert_Eliassen, apps.py:300-346 with apps.__mask_FS :2112-2159, apps.__coeffs_Eliassen :1582-1606
+ * and the de-masking of apps.__template :1386-1392, for icbc == None): A, B, C as the caller holds them (dense, or one
+ * slice shared by the batch through opts.coef_stride), the user's forcing with user_undef (any NaN when that is NaN)
+ * marking land; the masked forcing, the zero initial guess and the de-masked result (land = out_undef) are formed on
+ * the device.  S_out is output only.  XINV_E_UNSUPPORTED when an unmasked forcing value is not finite. */
+int xinv_std2d_front(xinv_ctx *ctx, double *S_out, const double *A, const double *B, const double *C,
+                     const double *F_user, double user_undef, double out_undef,
+                     int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                     double delxSqr, double ratioQtr, double ratioSqr, double optArg, double undef,
+                     double *flags, int64_t mxLoop, double tolerance, const xinv_opts *opts);
+
+/* ---- The remaining SOR kernels of numbas.py, on the generic colour engine ---------------------
  * Same conventions as above (batch axis first, S in/out, flags[batch][3], opts may be NULL; XINV_ORDER_COLOUR
  * only).  Each mirrors the numba signature it replaces, minus the arguments that kernel never reads:
  *   xinv_std2d_test  numbas.invert_standard_2D_test (numbas.py:421-424): nine-point stencil with two cross-term

@@ -1,4 +1,3 @@
 #!/bin/bash
 OUT=gpurun_out/${1:-r2s}; mkdir -p $OUT
-timeout 600 python -m pytest tests/test_gpu_more_kernels.py tests/test_gpu_resident.py -q -x --timeout 120 2>&1 | tail -12
-python scripts/prof_resident.py 2000 | tail -1
+timeout 600 python -m pytest tests/test_gpu_apps.py -q -x --timeout 120 2>&1 | tail -12

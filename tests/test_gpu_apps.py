@@ -201,6 +201,48 @@ def test_eliassen_nine_point_bit_exact_vs_oracle(gpu_ctx):
     assert np.array_equal(s_g.values, s_o.values)
 
 
+@pytest.mark.parametrize("coef_dims", ["core", "full", "mixed"])
+def test_eliassen_device_front_end_equals_host_path(gpu_ctx, monkeypatch, coef_dims):
+    """invert_Eliassen with icbc=None goes through xinv_std2d_front (masks, zero guess, de-masking on the device; the
+    coefficient fields handed over as the user holds them, core-shaped ones shared by the batch); the reference-shaped
+    host path must give the same bits: NaN-marked land, a batch over time, every form of A / B / C."""
+    from xinvert_b200 import apps
+    T, ny, nx = 5, 37, 73
+    z, y = np.linspace(100000., 10000., ny), np.linspace(-80., 80., nx)
+    co = {'time': np.arange(T), 'lev': z, 'lat': y}
+    rng = np.random.default_rng(8)
+    core_co = {'lev': z, 'lat': y}
+    mk = lambda v, full: DA(v, ['time', 'lev', 'lat'], co) if full else DA(v, ['lev', 'lat'], core_co)
+    full = {"core": (False, False, False), "full": (True, True, True), "mixed": (True, False, False)}[coef_dims]
+    shp = lambda f: (T, ny, nx) if f else (ny, nx)
+    A = mk(1 + 0.2 * rng.random(shp(full[0])), full[0])
+    B = mk(0.1 * rng.standard_normal(shp(full[1])), full[1])
+    C = DA(1 + 0.2 * rng.random(ny), ['lev'], {'lev': z}) if coef_dims == "mixed" else mk(1 + 0.2 * rng.random(shp(full[2])), full[2])
+    Fv = 1e-9 * rng.standard_normal((T, ny, nx))
+    Fv[:, 30:, 20:30] = np.nan                                     # topography
+    F = DA(Fv, ['time', 'lev', 'lat'], co)
+    ip = {'BCs': ['fixed', 'fixed'], 'mxLoop': 300, 'tolerance': 1e-9, 'optArg': 1.2, 'printInfo': False}
+    kw = dict(dims=['lev', 'lat'], coords='z-lat', mParams={'A': A, 'B': B, 'C': C})
+    calls = []
+    real = apps._device_solvers.solve_standard_2D_front
+    monkeypatch.setattr(apps._device_solvers, "solve_standard_2D_front", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    ip_f = dict(ip)
+    s_f = xb.invert_Eliassen(F, iParams=ip_f, **kw)
+    assert calls, "the device front end was not used"
+    assert gpu_ctx.stats()["engine"] == "resident" and ip_f['stats']['h2d_bytes'] < 8 * (Fv.size * (1 + sum(full)) + 3 * ny * nx) + 4096
+    monkeypatch.setattr(apps, "_eliassen_device_front", lambda *a, **k: None)
+    ip_h = dict(ip)
+    s_h = xb.invert_Eliassen(F, iParams=ip_h, **kw)
+    assert np.array_equal(s_f.values, s_h.values, equal_nan=True)
+    assert np.array_equal(ip_f['flags_all'][:, [0, 2]], ip_h['flags_all'][:, [0, 2]])
+    assert np.isnan(s_f.values[:, 30:, 20:30]).all() and np.isfinite(s_f.values[:, :30]).all()
+    # an unmasked non-finite forcing value: falls back to the host path (which reproduces the reference's NaN smear)
+    Fv2 = Fv.copy(); Fv2[0, 5, 5] = np.inf
+    monkeypatch.undo()
+    s_bad = xb.invert_Eliassen(DA(Fv2, ['time', 'lev', 'lat'], co), iParams=dict(ip), **kw)
+    assert s_bad.values.shape == Fv.shape
+
+
 def test_stommel_idealized_fused_general_form(gpu_ctx, capsys):
     """tests/test_StommelWBC.py:14-45 of the reference (general_2D halves): lexicographic ordering
     reproduces the reference's loop counts / maxima; the default ordering runs on the fused

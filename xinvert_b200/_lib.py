@@ -71,6 +71,7 @@ _STD2DT = [_vp] * 8 + [_i64, _i64, _i64, _int, _int] + [_dbl] * 5 + [_vp, _i64, 
 _GEN3D = [_vp] * 10 + [_i64, _i64, _i64, _i64, _int, _int, _int] + [_dbl] * 8 + [_vp, _i64, _dbl, _P(XinvOpts)]
 _STD1D = [_vp] * 5 + [_i64, _i64, _int] + [_dbl] * 3 + [_vp, _i64, _dbl, _P(XinvOpts)]
 _BIH2D = [_vp] * 12 + [_i64, _i64, _i64, _int, _int] + [_dbl] * 9 + [_vp, _i64, _dbl, _P(XinvOpts)]
+_STD2D_FRONT = [_vp] * 6 + [_dbl, _dbl, _i64, _i64, _i64, _int, _int] + [_dbl] * 5 + [_vp, _i64, _dbl, _P(XinvOpts)]
 SYMBOLS = [
     ("xinv_create", _int, [_P(_vp), _int]),
     ("xinv_create_on_stream", _int, [_P(_vp), _int, _vp]),
@@ -92,6 +93,7 @@ SYMBOLS = [
     ("xinv_flow2d", _int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _P(XinvFlowDesc), _P(XinvOpts)]),
     ("xinv_std2d", _int, _STD2D),
     ("xinv_std2d_rows", _int, _STD2D_ROWS),
+    ("xinv_std2d_front", _int, _STD2D_FRONT),
     ("xinv_gen2d_rows", _int, _GEN2D_ROWS),
     ("xinv_std3d_rows", _int, _STD3D_ROWS),
     ("xinv_gen2d", _int, _GEN2D),

@@ -87,7 +87,11 @@ def invert_Poisson(F, dims, coords='lat-lon', icbc=None,
 def invert_Eliassen(F, dims, coords='z-lat', icbc=None,
                     mParams=default_mParams, iParams=default_iParams):
     r"""Invert the Eliassen balanced-vortex equation with user-supplied
-    ``mParams['A'|'B'|'C']`` fields (apps.py:300-346); 9-point stencil."""
+    ``mParams['A'|'B'|'C']`` fields (apps.py:300-346); 9-point stencil.  With ``icbc=None`` the masks, the zero
+    initial guess and the de-masking are done on the device (``xinv_std2d_front``)."""
+    fast = _eliassen_device_front(F, dims, coords, icbc, mParams, iParams)
+    if fast is not None:
+        return fast
     return _template(_coeffs_Eliassen, core.inv_standard2D, 2, F, dims, coords,
                      icbc, ['A', 'B', 'C', 'g', 'Omega', 'Rearth'], mParams, iParams)
 
@@ -530,6 +534,54 @@ def _coeffs_Eliassen(g, coords, mParams, iParams, icbc):
     C = _user_field(g, zero, mParams['C'], 'C')
     Fm = np.where(maskF != _undeftmp, maskF, _undeftmp)
     return maskF, Fm, initS, (A, B, C)
+
+
+def _eliassen_device_front(F, dims, coords, icbc, mParams, iParams):
+    """invert_Eliassen through the dense device front end (xinv_std2d_front), or None when the reference-shaped host
+    path has to be taken (icbc given, core dims not trailing, lexicographic ordering, non-float64 input, a coefficient
+    whose dims are neither the core dims, all dims, one core dim nor a scalar).  Follows apps.__template
+    (apps.py:1324-1394) with apps.__coeffs_Eliassen (:1582-1606): the coefficient fields are handed over as the user
+    holds them (core-shaped ones shared by the whole batch), masks / zero guess / de-masking happen on the device."""
+    if icbc is not None or len(dims) != 2:
+        return None
+    ip = _update(default_iParams, iParams)
+    if ip.get('ordering', 'colour') not in ('colour', 'color', 'redblack', 'red-black') or core.solvers is not _device_solvers:
+        return None
+    mp = _update(default_mParams, mParams, ['A', 'B', 'C', 'g', 'Omega', 'Rearth'])
+    g = _Grid(F, dims)
+    if not g.trailing or g.values.dtype != np.float64 or coords.lower() not in ('z-lat', 'cartesian'):
+        return None
+
+    def field(X):                                # _user_field without the full-size zero template
+        if hasattr(X, 'dims'):
+            xd, xv = list(X.dims), np.ascontiguousarray(np.asarray(X.values, dtype=np.float64))
+            if xd == g.dims or (xd == g.all_dims and xd != g.dims):
+                return xv
+            if len(xd) == 1 and xd[0] in g.dims:
+                return np.ascontiguousarray(np.zeros(g.core_shape) + g.along(g.dims.index(xd[0]), xv, False))
+            return None
+        return np.zeros(g.core_shape) + float(X)
+
+    fields = [field(mp[k]) for k in ('A', 'B', 'C')]
+    if any(f is None for f in fields):
+        return None
+    ps = _cal_params2D(g, coords, mp['Rearth'])
+    ip = _update(ps, ip)
+    if ip['debug']:
+        _print_params(ip)
+    try:
+        S, flags, stats = _device_solvers.solve_standard_2D_front(
+            g.values, fields[0], fields[1], fields[2], ip['undef'], ip['undef'], ip['BCs'][0], ip['BCs'][1], ip['del1Sqr'],
+            ip['ratioQtr'], ip['ratioSqr'], ip['optArg'], _undeftmp, ip['flags'], ip['mxLoop'], ip['tolerance'],
+            engine=ip.get('engine', 'auto'), ctx=ip.get('ctx'), devices=ip.get('devices'), accel=ip.get('accel'))
+    except XinvError as e:
+        if e.code == E_UNSUPPORTED:              # e.g. a non-finite unmasked forcing value
+            return None
+        raise
+    _, noncore, _ = core._layout(F, dims)
+    core._report(ip, core._slice_labels(F, noncore), flags)
+    _report_flags(iParams, flags, stats)
+    return wrap_like(F, S, name='inverted')
 
 
 def _rows_GillMatsuno(g, coords, mParams):

@@ -86,6 +86,9 @@ struct Problem {
     ResidentPlan resident{};     // small 2-D slices (xinv_resident.cuh)
     ClusterPlan cluster{};       // small / medium 2-D slices with row coefficients, on top of `fused` (xinv_cluster2d.cuh)
     bool front = false;          // xinv_std2d_rows: S is output only, de-masked on the device
+    bool maskfront = false;      // xinv_std2d_front: dense coefficients, the user's forcing masked / the result de-masked on the device
+    const double *dFmask = nullptr;   // ... its masked forcing (device)
+    double out_undef = 0.0;
     int io_f32 = 0;              // XINV_IO_F32_* (front ends, host pointers)
     int accel = 0;               // XINV_ACCEL_*
     double rho2 = 0.0;           // Chebyshev: squared Jacobi spectral radius implied by optArg
@@ -295,6 +298,27 @@ extern "C" int xinv_memcpy_d2h(xinv_ctx *c, void *dst, const void *src, int64_t 
     return XINV_OK;
 }
 
+// Dense front end (xinv_std2d_front: invert_Eliassen): what apps.__mask_FS and the de-masking of apps.__template do on
+// full-size host arrays (apps.py:2112-2159, :1386-1392), on the device -- land (F == user_undef, any NaN when that is NaN)
+// becomes the internal undef in the forcing, the initial guess is zero; afterwards land becomes out_undef in the result.
+// flag[1] |= 1 when an unmasked forcing value is not finite (the caller falls back to the host-built path then).
+__global__ void xd_front_mask_kernel(double *__restrict__ F, double *__restrict__ S, i64 n, double user_undef, double undef,
+                                     int *__restrict__ flag)
+{
+    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double f = F[p];
+    const bool land = ((user_undef != user_undef) ? (f != f) : (f == user_undef)) | (f == undef);
+    if (land) F[p] = undef;
+    else if (!isfinite(f)) flag[1] = 1;
+    S[p] = 0.0;
+}
+__global__ void xd_front_demask_kernel(double *__restrict__ S, const double *__restrict__ F, i64 n, double undef, double out_undef)
+{
+    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n && F[p] == undef) S[p] = out_undef;
+}
+
 // float32 I/O of the front ends (xinv_opts.io_f32): widen after the H2D copy, narrow before the D2H copy
 __global__ void xd_widen_kernel(double *__restrict__ dst, const float *__restrict__ src, i64 n)
 {
@@ -349,6 +373,7 @@ struct BeginArgs {
     const xinv_opts *opts;
     // xinv_std2d_rows (front end): coef[0] = A rows [ny], coef[2] = C rows [ny], coef[3] = user forcing
     bool front = false;
+    bool maskfront = false;  // xinv_std2d_front: dense A, B, C; coef[3] = the user's forcing (S is output only)
     const double *f_scale = nullptr;
     double user_undef = 0.0, out_undef = 0.0;
     // xinv_gen2d_rows: coef[0] = rows [5][ny], coef[6] = user forcing
@@ -564,8 +589,10 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
         int rc = ensure(c->stage[0], slice_bytes * a.batch);
         if (rc) return rc;
         pb.dS = (double *)c->stage[0].p;
-        CK(cudaMemcpyAsync(pb.dS, a.S, slice_bytes * a.batch, cudaMemcpyHostToDevice, c->stream));
-        c->stats.h2d_bytes += (i64)(slice_bytes * a.batch);
+        if (!a.maskfront) {                                          // (S is output only there: zeroed by the mask kernel)
+            CK(cudaMemcpyAsync(pb.dS, a.S, slice_bytes * a.batch, cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2d_bytes += (i64)(slice_bytes * a.batch);
+        }
         for (int m = 0; m < a.ncoef; ++m) {
             if (!a.coef[m]) { pb.q.c[m] = nullptr; pb.q.cs[m] = 0; continue; }
             const i64 stride = (m >= 8 || o.coef_stride[m] < 0) ? g.N : o.coef_stride[m];      // (xinv_opts has eight strides)
@@ -589,6 +616,29 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
             pb.q.c[m] = a.coef[m];
             pb.q.cs[m] = (!a.coef[m]) ? 0 : ((m >= 8 || o.coef_stride[m] < 0) ? g.N : o.coef_stride[m]);
         }
+    }
+
+    if (a.maskfront) {
+        // the forcing is masked in a buffer of our own (never in the caller's device array), S starts from zero
+        pb.maskfront = true;
+        pb.out_undef = a.out_undef;
+        if (pb.q.cs[3] != g.N) return set_err(XINV_E_ARG, "xinv_std2d_front: the forcing needs one slice per batch entry");
+        const i64 n = g.N * a.batch;
+        double *dF;
+        if (pb.mem_space == XINV_MEM_HOST) dF = (double *)c->stage[2 + 3].p;
+        else {
+            int rc_ = ensure(c->stage[2 + 3], slice_bytes * a.batch);
+            if (rc_) return rc_;
+            dF = (double *)c->stage[2 + 3].p;
+            CK(cudaMemcpyAsync(dF, a.coef[3], slice_bytes * a.batch, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        int rc_ = xm_work_ensure(c->xm_work, 7, 16) == cudaSuccess ? XINV_OK : XINV_E_NOMEM;
+        if (rc_) return set_err(rc_, "flag buffer");
+        CK(cudaMemsetAsync(c->xm_work.p[7], 0, 8, c->stream));
+        xd_front_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(dF, pb.dS, n, a.user_undef, a.undef, (int *)c->xm_work.p[7]);
+        c->stats.kernel_launches++;
+        pb.q.c[3] = dF;
+        pb.dFmask = dF;
     }
 
     int rc;
@@ -683,7 +733,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));       // a.flags (caller's host memory) has been read
-    if (a.front) {                              // did the front end meet a non-finite unmasked forcing value?
+    if (a.front || a.maskfront) {               // did the front end meet a non-finite unmasked forcing value?
         int fl[2] = {0, 0};
         CK(cudaMemcpy(fl, c->xm_work.p[7], sizeof fl, cudaMemcpyDeviceToHost));
         if (fl[1]) {
@@ -922,6 +972,11 @@ extern "C" int xinv_end(xinv_ctx *c)
         c->stats.kernel_launches++;
         CK(cudaGetLastError());
     }
+    if (pb.maskfront) {
+        const i64 n = g.N * pb.batch;
+        xd_front_demask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(pb.dS, pb.dFmask, n, pb.q.undef, pb.out_undef);
+        c->stats.kernel_launches++;
+    }
     std::vector<XdSliceState> hs((size_t)pb.batch);
     CK(cudaEventRecord(c->ev0, c->stream));
     if (pb.mem_space == XINV_MEM_HOST && (pb.io_f32 & XINV_IO_F32_OUT)) {
@@ -1083,6 +1138,26 @@ extern "C" int xinv_std3d_begin(xinv_ctx *ctx, double *S, const double *A, const
     a.p[0] = delxSqr; a.p[1] = ratio2Sqr; a.p[2] = ratio1Sqr;
     a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
     return problem_begin(ctx, a);
+}
+
+// invert_Eliassen's front end: dense (or batch-shared) A, B, C and the user's forcing; masks, zero initial guess and
+// de-masking on the device.  Any engine the dense entry would use (resident for small sections, colour, marching).
+extern "C" int xinv_std2d_front(xinv_ctx *ctx, double *S_out, const double *A, const double *B, const double *C,
+                                const double *F_user, double user_undef, double out_undef,
+                                int64_t batch, int64_t ny, int64_t nx, int bcy, int bcx,
+                                double delxSqr, double ratioQtr, double ratioSqr, double optArg, double undef,
+                                double *flags, int64_t mxLoop, double tolerance, const xinv_opts *opts)
+{
+    BeginArgs a{};
+    a.kind = XD_STD2D; a.S = S_out;
+    a.coef[0] = A; a.coef[1] = B; a.coef[2] = C; a.coef[3] = F_user; a.ncoef = 4; a.b_index = 1;
+    a.batch = batch; a.nz = 1; a.ny = ny; a.nx = nx; a.bcy = bcy; a.bcx = bcx;
+    a.p[0] = delxSqr; a.p[1] = ratioQtr; a.p[2] = ratioSqr;
+    a.optArg = optArg; a.undef = undef; a.flags = flags; a.mxLoop = mxLoop; a.tol = tolerance; a.opts = opts;
+    a.maskfront = true; a.user_undef = user_undef; a.out_undef = out_undef;
+    int rc = problem_begin(ctx, a);
+    if (rc) return rc;
+    return run_to_completion(ctx);
 }
 
 // ---- the remaining kernels of numbas.py (colour engine) ----

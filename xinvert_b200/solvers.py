@@ -360,6 +360,37 @@ def solve_standard_2D_rows(F_user, A_rows, C_rows, F_row_scale, user_undef, out_
     return S, fl, stats
 
 
+def solve_standard_2D_front(F_user, A, B, C_, user_undef, out_undef, BCy, BCx, delxSqr, ratioQtr, ratioSqr, optArg,
+                            undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000, tolerance=1e-8, engine="auto", check_every=0,
+                            ctx=None, devices=None, accel=None):
+    """Dense front end (``xinv_std2d_front``; invert_Eliassen): the user's forcing ``F_user[..., ny, nx]`` (host numpy
+    array; cells equal to ``user_undef`` -- any NaN when that is NaN -- are land) and the coefficient arrays A, B
+    (``None`` = 0), C as the caller holds them: S's shape, or one ``[ny, nx]`` slice shared by the batch.  Returns
+    ``(S, flags[batch, 3], stats)``: solved from a zero initial guess, land set to ``out_undef`` (what apps.__mask_FS and
+    apps.__template's de-masking do on full-size host arrays happens on the device)."""
+    L = _lib.load()
+    Fh = _host_f64(F_user, "F")
+    S = _lib.pinned_empty(Fh.shape)
+    B = _zero_to_none(B)
+    ops = _Operands(S, [("A", A), ("B", B), ("C", C_), ("F", Fh)], 2)
+    ny, nx = ops.core
+    fl = _flags_array(flags, ops.batch)
+
+    def call(c, lo, hi):
+        opts = _lib.make_opts(mem_space=_lib.MEM_HOST, engine=engine, check_every=check_every, coef_strides=ops.strides, accel=accel)
+        off = lambda p, stride: C.c_void_p(p + 8 * lo * stride) if p is not None else None
+        ptr = [off(p, st) for p, st in zip(ops.ptrs, ops.strides)]
+        rc = L.xinv_std2d_front(c.handle, off(ops.S_ptr, ops.N), ptr[0], ptr[1], ptr[2], ptr[3], float(user_undef),
+                                float(out_undef), hi - lo, ny, nx, _lib.BC_CODES[BCy], _lib.BC_CODES[BCx], float(delxSqr),
+                                float(ratioQtr), float(ratioSqr), float(optArg), float(undef),
+                                C.c_void_p(fl[lo:hi].ctypes.data), int(mxLoop), float(tolerance), C.byref(opts))
+        _lib.check(rc)
+        return c.stats()
+
+    stats = _execute(call, ops.batch, ops.N, ctx, devices, host=True)
+    return S, fl, stats
+
+
 def solve_general_2D_rows(G_user, rows, g_mode, g_p1, g_p2, user_undef, out_undef, BCy, BCx, delx, delxSqr, ratio,
                           ratioQtr, ratioSqr, optArg, undef=_UNDEF, flags=(0.0, 1.0, 0.0), mxLoop=5000,
                           tolerance=1e-8, check_every=0, ctx=None, devices=None, accel=None):
