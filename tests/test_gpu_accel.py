@@ -78,7 +78,7 @@ def test_chebyshev_to_tolerance_same_fixed_point(gpu_ctx):
     om = c["p"]["optArg"]
     S_p, f_p = cases.run_std2d(xb, c, "fixed", "periodic", 9000, 1e-10, omega=om)
     S_a, f_a = cases.run_std2d(xb, c, "fixed", "periodic", 9000, 1e-10, omega=om, accel="chebyshev")
-    assert gpu_ctx.stats()["engine"] == "cluster"
+    assert gpu_ctx.stats()["engine"] in ("cluster", "colour")      # (colour where the device cannot host a 16-CTA cluster)
     S_o, f_o = cases.run_std2d(oracle, c, "fixed", "periodic", 9000, 1e-10, omega=om, ordering="chebyshev")
     assert np.array_equal(S_a, S_o)
     _check_flags(f_a, f_o)
