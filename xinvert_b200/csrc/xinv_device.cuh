@@ -100,6 +100,41 @@ __device__ __forceinline__ void xd_update_std2d(double *__restrict__ S,
     S[c] = Sc + temp;
 }
 
+// The same update with everything that does not change between sweeps formed beforehand, by the reference's own
+// operations (as the marching engines do): Fd = F * delxSqr, or a marker NaN (high word XD_SKIP_HI) where the cell must
+// never be updated; fac = optArg / denominator.  Same operations on the same operands as xd_update_std2d: same bits.
+#define XD_SKIP_HI 0x7ff4dead
+template <bool HASB>
+__device__ __forceinline__ void xd_update_std2d_pre(double *__restrict__ S,
+    const double *__restrict__ A, const double *__restrict__ B, const double *__restrict__ C,
+    const double *__restrict__ Fd, const double *__restrict__ fac,
+    int nx, int j, int i, int ip, int im, double ratioQtr, double ratioSqr)
+{
+    const int c = j * nx + i, n = c + nx, s = c - nx;
+    const int e = j * nx + ip, w = j * nx + im;
+    const double Fdc = Fd[c];
+    if (__double2hiint(Fdc) == XD_SKIP_HI) return;
+    const double An = A[n], Ac = A[c], Ce = C[e], Cc = C[c];
+    const double Sc = S[c], Sn = S[n], Ss = S[s], Se = S[e], Sw = S[w];
+    const double t1 = (An * (Sn - Sc) - Ac * (Sc - Ss)) * ratioSqr;
+    const double t4 = (Ce * (Se - Sc) - Cc * (Sc - Sw));
+    double temp;
+    if (HASB) {
+        const double Be = B[e], Bw = B[w], Bn = B[n], Bs = B[s];
+        const double Bq = (i == 0) ? B[n + 1] : Bn;            // numbas.py:327 west-column quirk
+        const double Sne = S[n - i + ip], Snw = S[n - i + im];
+        const double Sse = S[s - i + ip], Ssw = S[s - i + im];
+        const double Sse2 = (i == 0) ? Ss : Sse;               // numbas.py:328 west-column quirk
+        const double t2 = (Bq * (Sne - Snw) - Bs * (Sse2 - Ssw)) * ratioQtr;
+        const double t3 = (Be * (Sne - Sse) - Bw * (Snw - Ssw)) * ratioQtr;
+        temp = (((t1 + t2) + t3) + t4) - Fdc;
+    } else {
+        temp = (t1 + t4) - Fdc;
+    }
+    temp = temp * fac[c];
+    S[c] = Sc + temp;
+}
+
 // general 2-D.  c[] = {A,B,C,D,E,F,G}; p[] = {delx, delxSqr, ratio, ratioQtr, ratioSqr}
 template <bool HASB>
 __device__ __forceinline__ void xd_update_gen2d(double *__restrict__ S,

@@ -44,7 +44,9 @@ struct XrArgs {
     double rho2;
 };
 
-template <int KIND, bool HASB>
+// PRE (standard form, no omega schedule, one more array fits): after staging, F is replaced in place by Fd and a
+// factor array is formed once per launch (xd_update_std2d_pre) -- no undef test and no division in the sweeps.
+template <int KIND, bool HASB, bool PRE>
 __global__ void __launch_bounds__(XR_THREADS, 1)
 xr_resident_kernel(const XrArgs a)
 {
@@ -54,7 +56,7 @@ xr_resident_kernel(const XrArgs a)
     const i64 Np = (N + 1) & ~(i64)1;            // arrays start 16-byte aligned
     double *sm = reinterpret_cast<double *>(xr_smem);
     double *sS = sm;
-    double *red_sum = sm + (size_t)(a.narr + 1) * Np;          // [32]
+    double *red_sum = sm + (size_t)(a.narr + 1 + (PRE ? 1 : 0)) * Np;   // [32]  (PRE: the factor array sits before it)
     i64 *red_cnt = reinterpret_cast<i64 *>(red_sum + 32);       // [32]
     uint64_t *bar = reinterpret_cast<uint64_t *>(red_cnt + 32);
     int *flag = reinterpret_cast<int *>(bar + 1);
@@ -116,6 +118,28 @@ xr_resident_kernel(const XrArgs a)
         const double *c5 = (KIND == XD_GEN2D) ? sm + (size_t)a.slot[5] * Np : nullptr;
         const double *c6 = (KIND == XD_GEN2D) ? sm + (size_t)a.slot[6] * Np : nullptr;
 
+        double *sFac = sm + (size_t)(a.narr + 1) * Np;          // PRE only
+        if (PRE) {
+            double *sF = sm + (size_t)a.slot[3] * Np;
+            for (int p = tid; p < (int)N; p += nth) {
+                const int j = p / (int)nx, i = p - j * (int)nx;
+                double fdv = __hiloint2double(XD_SKIP_HI, 0), fv = 0.0;
+                if (j >= 1 && j <= (int)ny - 2 && i >= g.i0 && i < g.i1) {
+                    const int ip = (i == (int)nx - 1) ? 0 : i + 1, im = (i == 0) ? (int)nx - 1 : i - 1;
+                    const int n = p + (int)nx, s = p - (int)nx, e = j * (int)nx + ip, w = j * (int)nx + im;
+                    const double Fc = sF[p], An = cA[n], Ac = cA[p], Ce = c2[e], Cc = c2[p];
+                    bool cond = (Fc != undef) & (An != undef) & (Ac != undef) & (Ce != undef) & (Cc != undef);
+                    if (HASB) cond = cond & (cB[e] != undef) & (cB[w] != undef) & (cB[n] != undef) & (cB[s] != undef);
+                    if (cond) {
+                        fdv = Fc * a.q.p[0];
+                        fv = a.q.optArg / ((An + Ac) * a.q.p[2] + (Ce + Cc));
+                    }
+                }
+                sF[p] = fdv;                                 // (a cell's condition reads F at the cell itself only)
+                sFac[p] = fv;
+            }
+            __syncthreads();
+        }
         XdSliceState st_;
         if (tid == 0) st_ = a.st[b];
         double om = a.st[b].omega;                   // Chebyshev: factor of the next half sweep (every thread keeps it)
@@ -143,7 +167,9 @@ xr_resident_kernel(const XrArgs a)
                         const i64 i = nx - 1;
                         if (i < g.i0 || i >= g.i1) continue;
                         if (xd_colour(g.scheme, g.wrapfix, nx, j, j, i) != colour) continue;
-                        if (KIND == XD_STD2D)
+                        if (KIND == XD_STD2D && PRE)
+                            xd_update_std2d_pre<HASB>(sS, cA, cB, c2, c3, sFac, (int)nx, j, (int)i, 0, (int)i - 1, a.q.p[1], a.q.p[2]);
+                        else if (KIND == XD_STD2D)
                             xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, 0, i - 1, a.q.p[0], a.q.p[1], a.q.p[2], wq, undef);
                         else
                             xd_update_gen2d<HASB>(sS, cA, cB, c2, c3, c4, c5, c6, nx, j, i, 0, i - 1, a.q.p[0], a.q.p[1], a.q.p[2],
@@ -160,7 +186,9 @@ xr_resident_kernel(const XrArgs a)
                         if (xd_colour(g.scheme, g.wrapfix, nx, j, j, i) != colour) continue;
                         const i64 ip = (i == (int)nx - 1) ? 0 : i + 1;
                         const i64 im = (i == 0) ? nx - 1 : i - 1;
-                        if (KIND == XD_STD2D)
+                        if (KIND == XD_STD2D && PRE)
+                            xd_update_std2d_pre<HASB>(sS, cA, cB, c2, c3, sFac, (int)nx, j, i, (int)ip, (int)im, a.q.p[1], a.q.p[2]);
+                        else if (KIND == XD_STD2D)
                             xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2], wq, undef);
                         else
                             xd_update_gen2d<HASB>(sS, cA, cB, c2, c3, c4, c5, c6, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2],
@@ -205,20 +233,21 @@ xr_resident_kernel(const XrArgs a)
 struct ResidentPlan {
     bool built = false;
     XrArgs args{};
-    size_t smem = 0;
+    size_t smem = 0, smem_pre = 0;   // without / with the factor array of the PRE kernels
     int grid = 0;
     int kind = 0;
     bool hasB = false;
+    bool pre_ok = false;             // the PRE kernel fits (standard form)
 };
 
 static inline void resident_plan_release(ResidentPlan &p) { p = ResidentPlan(); }
 
-template <int KIND, bool HASB>
+template <int KIND, bool HASB, bool PRE>
 static cudaError_t xr_prepare(size_t smem, int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(xr_resident_kernel<KIND, HASB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(xr_resident_kernel<KIND, HASB, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, xr_resident_kernel<KIND, HASB>, XR_THREADS, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, xr_resident_kernel<KIND, HASB, PRE>, XR_THREADS, smem);
 }
 
 // Does a slice with all its operands fit into the shared memory of one SM?
@@ -241,8 +270,15 @@ static inline int resident_plan_build(ResidentPlan &p, int sm_count, int kind, b
     if (p.smem > 220 * 1024) { why = "slice does not fit into shared memory"; return -1; }
     int bps = 0;
     cudaError_t e;
-    if (kind == XD_STD2D) e = hasB ? xr_prepare<XD_STD2D, true>(p.smem, &bps) : xr_prepare<XD_STD2D, false>(p.smem, &bps);
-    else                  e = hasB ? xr_prepare<XD_GEN2D, true>(p.smem, &bps) : xr_prepare<XD_GEN2D, false>(p.smem, &bps);
+    if (kind == XD_STD2D) e = hasB ? xr_prepare<XD_STD2D, true, false>(p.smem, &bps) : xr_prepare<XD_STD2D, false, false>(p.smem, &bps);
+    else                  e = hasB ? xr_prepare<XD_GEN2D, true, false>(p.smem, &bps) : xr_prepare<XD_GEN2D, false, false>(p.smem, &bps);
+    p.smem_pre = p.smem + (size_t)Np * sizeof(double);
+    if (e == cudaSuccess && bps >= 1 && kind == XD_STD2D && p.smem_pre <= 220 * 1024 && g.N < ((i64)1 << 30)) {
+        int bps2 = 0;
+        cudaError_t e2 = hasB ? xr_prepare<XD_STD2D, true, true>(p.smem_pre, &bps2) : xr_prepare<XD_STD2D, false, true>(p.smem_pre, &bps2);
+        p.pre_ok = (e2 == cudaSuccess && bps2 >= 1);
+        if (!p.pre_ok) (void)cudaGetLastError();
+    }
     if (e != cudaSuccess || bps < 1) { why = std::string("resident kernel does not fit: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return -1; }
     a.S = dS; a.q = q; a.g = g; a.batch = (int)batch;
     const i64 slots = (i64)sm_count * bps;
@@ -258,12 +294,15 @@ static inline int resident_sweep(ResidentPlan &p, cudaStream_t stream, XdSliceSt
     XrArgs &a = p.args;
     a.st = st; a.nactive = nactive; a.tol = tol; a.mxLoop = mxLoop; a.zero_exit = zero_exit; a.nsweeps = nsweeps;
     a.accel = accel; a.rho2 = rho2;
-    if (p.kind == XD_STD2D) {
-        if (p.hasB) xr_resident_kernel<XD_STD2D, true><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
-        else        xr_resident_kernel<XD_STD2D, false><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
+    if (p.kind == XD_STD2D && p.pre_ok && !accel) {
+        if (p.hasB) xr_resident_kernel<XD_STD2D, true, true><<<p.grid, XR_THREADS, p.smem_pre, stream>>>(a);
+        else        xr_resident_kernel<XD_STD2D, false, true><<<p.grid, XR_THREADS, p.smem_pre, stream>>>(a);
+    } else if (p.kind == XD_STD2D) {
+        if (p.hasB) xr_resident_kernel<XD_STD2D, true, false><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
+        else        xr_resident_kernel<XD_STD2D, false, false><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
     } else {
-        if (p.hasB) xr_resident_kernel<XD_GEN2D, true><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
-        else        xr_resident_kernel<XD_GEN2D, false><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
+        if (p.hasB) xr_resident_kernel<XD_GEN2D, true, false><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
+        else        xr_resident_kernel<XD_GEN2D, false, false><<<p.grid, XR_THREADS, p.smem, stream>>>(a);
     }
     *launches += 1;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
