@@ -104,14 +104,20 @@ __device__ __forceinline__ void xd_update_std2d(double *__restrict__ S,
 // operations (as the marching engines do): Fd = F * delxSqr, or a marker NaN (high word XD_SKIP_HI) where the cell must
 // never be updated; fac = optArg / denominator.  Same operations on the same operands as xd_update_std2d: same bits.
 #define XD_SKIP_HI 0x7ff4dead
+// Storage: a row holds its even columns first, then its odd ones (XD_SPLIT_POS) -- the cells of one colour of a row
+// are contiguous, so a warp's loads of a colour step are unit-stride instead of stride-2 (no shared-memory bank
+// conflicts); he = (nx + 1) / 2.
+#define XD_SPLIT_POS(i, he) (((i) >> 1) + ((i) & 1) * (he))
 template <bool HASB>
 __device__ __forceinline__ void xd_update_std2d_pre(double *__restrict__ S,
     const double *__restrict__ A, const double *__restrict__ B, const double *__restrict__ C,
     const double *__restrict__ Fd, const double *__restrict__ fac,
-    int nx, int j, int i, int ip, int im, double ratioQtr, double ratioSqr)
+    int nx, int he, int j, int i, int ip, int im, double ratioQtr, double ratioSqr)
 {
-    const int c = j * nx + i, n = c + nx, s = c - nx;
-    const int e = j * nx + ip, w = j * nx + im;
+    const int row = j * nx;
+    const int pi = XD_SPLIT_POS(i, he), pe = XD_SPLIT_POS(ip, he), pw = XD_SPLIT_POS(im, he);
+    const int c = row + pi, n = c + nx, s = c - nx;
+    const int e = row + pe, w = row + pw;
     const double Fdc = Fd[c];
     if (__double2hiint(Fdc) == XD_SKIP_HI) return;
     const double An = A[n], Ac = A[c], Ce = C[e], Cc = C[c];
@@ -121,9 +127,9 @@ __device__ __forceinline__ void xd_update_std2d_pre(double *__restrict__ S,
     double temp;
     if (HASB) {
         const double Be = B[e], Bw = B[w], Bn = B[n], Bs = B[s];
-        const double Bq = (i == 0) ? B[n + 1] : Bn;            // numbas.py:327 west-column quirk
-        const double Sne = S[n - i + ip], Snw = S[n - i + im];
-        const double Sse = S[s - i + ip], Ssw = S[s - i + im];
+        const double Bq = (i == 0) ? B[row + nx + XD_SPLIT_POS(1, he)] : Bn;   // numbas.py:327 west-column quirk: B[j+1,1]
+        const double Sne = S[e + nx], Snw = S[w + nx];
+        const double Sse = S[e - nx], Ssw = S[w - nx];
         const double Sse2 = (i == 0) ? Ss : Sse;               // numbas.py:328 west-column quirk
         const double t2 = (Bq * (Sne - Snw) - Bs * (Sse2 - Ssw)) * ratioQtr;
         const double t3 = (Be * (Sne - Sse) - Bw * (Snw - Ssw)) * ratioQtr;

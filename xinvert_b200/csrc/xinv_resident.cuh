@@ -45,7 +45,9 @@ struct XrArgs {
 };
 
 // PRE (standard form, no omega schedule, one more array fits): after staging, F is replaced in place by Fd and a
-// factor array is formed once per launch (xd_update_std2d_pre) -- no undef test and no division in the sweeps.
+// factor array is formed once per launch (xd_update_std2d_pre) -- no undef test and no division in the sweeps -- and
+// every array is kept colour-split in shared memory (XD_SPLIT_POS: a row's even columns, then its odd ones), so that
+// the loads of a colour step are unit-stride across a warp instead of stride-2 (two-way bank conflicts on every LDS.64).
 template <int KIND, bool HASB, bool PRE>
 __global__ void __launch_bounds__(XR_THREADS, 1)
 xr_resident_kernel(const XrArgs a)
@@ -69,6 +71,8 @@ xr_resident_kernel(const XrArgs a)
     const int base = (g.scheme == 4) ? 4 : 2;
     const i64 half = (nx + 1) / 2;
     const double undef = a.q.undef;
+    const int he = ((int)nx + 1) / 2;            // PRE: even columns of a row first, then the odd ones
+    #define XR_POS(i) (PRE ? XD_SPLIT_POS((int)(i), he) : (int)(i))
     // thread layout of a colour step: W lanes per row, rpp rows at a time
     int W = ((int)half + 7) & ~7;
     if (W > nth) W = nth;
@@ -94,7 +98,7 @@ xr_resident_kernel(const XrArgs a)
             ++na;
         }
         const uint32_t nb16 = (uint32_t)((N / 2) * 16);          // bytes that can go as one bulk copy per array
-        bool bulk = nb16 >= 16;
+        bool bulk = nb16 >= 16 && !PRE;                          // (PRE: permuted on the way in, by ordinary loads)
         for (int m = 0; m < na; ++m) bulk = bulk && ((reinterpret_cast<uintptr_t>(src[m]) & 15) == 0);
         if (bulk) {
             if (tid == 0) {
@@ -105,6 +109,12 @@ xr_resident_kernel(const XrArgs a)
             if ((N & 1) && tid < na) dst[tid][N - 1] = src[tid][N - 1];     // the odd tail
             xf_mbar_wait(bar, phase);
             phase ^= 1u;
+        } else if (PRE) {
+            for (int p = tid; p < (int)N; p += nth) {
+                const int j = p / (int)nx, i = p - j * (int)nx;
+                const int pp = j * (int)nx + XD_SPLIT_POS(i, he);
+                for (int m = 0; m < na; ++m) dst[m][pp] = src[m][p];
+            }
         } else {
             for (int m = 0; m < na; ++m)
                 for (i64 p = tid; p < N; p += nth) dst[m][p] = src[m][p];
@@ -124,10 +134,11 @@ xr_resident_kernel(const XrArgs a)
             for (int p = tid; p < (int)N; p += nth) {
                 const int j = p / (int)nx, i = p - j * (int)nx;
                 double fdv = __hiloint2double(XD_SKIP_HI, 0), fv = 0.0;
+                const int pc = j * (int)nx + XD_SPLIT_POS(i, he);
                 if (j >= 1 && j <= (int)ny - 2 && i >= g.i0 && i < g.i1) {
                     const int ip = (i == (int)nx - 1) ? 0 : i + 1, im = (i == 0) ? (int)nx - 1 : i - 1;
-                    const int n = p + (int)nx, s = p - (int)nx, e = j * (int)nx + ip, w = j * (int)nx + im;
-                    const double Fc = sF[p], An = cA[n], Ac = cA[p], Ce = c2[e], Cc = c2[p];
+                    const int n = pc + (int)nx, s = pc - (int)nx, e = j * (int)nx + XD_SPLIT_POS(ip, he), w = j * (int)nx + XD_SPLIT_POS(im, he);
+                    const double Fc = sF[pc], An = cA[n], Ac = cA[pc], Ce = c2[e], Cc = c2[pc];
                     bool cond = (Fc != undef) & (An != undef) & (Ac != undef) & (Ce != undef) & (Cc != undef);
                     if (HASB) cond = cond & (cB[e] != undef) & (cB[w] != undef) & (cB[n] != undef) & (cB[s] != undef);
                     if (cond) {
@@ -135,8 +146,8 @@ xr_resident_kernel(const XrArgs a)
                         fv = a.q.optArg / ((An + Ac) * a.q.p[2] + (Ce + Cc));
                     }
                 }
-                sF[p] = fdv;                                 // (a cell's condition reads F at the cell itself only)
-                sFac[p] = fv;
+                sF[pc] = fdv;                                // (a cell's condition reads F at the cell itself only)
+                sFac[pc] = fv;
             }
             __syncthreads();
         }
@@ -152,9 +163,9 @@ xr_resident_kernel(const XrArgs a)
                 for (i64 i = tid; i < nx; i += nth) {
                     i64 s_ = i;
                     if (g.bcx != XD_BC_PERIODIC) { if (i == 0) s_ = 1; else if (i == nx - 1) s_ = nx - 2; }
-                    const double v0 = sS[nx + s_], v1 = sS[(ny - 2) * nx + s_];
-                    if (v0 != undef) sS[i] = v0;
-                    if (v1 != undef) sS[(ny - 1) * nx + i] = v1;
+                    const double v0 = sS[nx + XR_POS(s_)], v1 = sS[(ny - 2) * nx + XR_POS(s_)];
+                    if (v0 != undef) sS[XR_POS(i)] = v0;
+                    if (v1 != undef) sS[(ny - 1) * nx + XR_POS(i)] = v1;
                 }
                 __syncthreads();
             }
@@ -168,7 +179,7 @@ xr_resident_kernel(const XrArgs a)
                         if (i < g.i0 || i >= g.i1) continue;
                         if (xd_colour(g.scheme, g.wrapfix, nx, j, j, i) != colour) continue;
                         if (KIND == XD_STD2D && PRE)
-                            xd_update_std2d_pre<HASB>(sS, cA, cB, c2, c3, sFac, (int)nx, j, (int)i, 0, (int)i - 1, a.q.p[1], a.q.p[2]);
+                            xd_update_std2d_pre<HASB>(sS, cA, cB, c2, c3, sFac, (int)nx, he, j, (int)i, 0, (int)i - 1, a.q.p[1], a.q.p[2]);
                         else if (KIND == XD_STD2D)
                             xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, 0, i - 1, a.q.p[0], a.q.p[1], a.q.p[2], wq, undef);
                         else
@@ -187,7 +198,7 @@ xr_resident_kernel(const XrArgs a)
                         const i64 ip = (i == (int)nx - 1) ? 0 : i + 1;
                         const i64 im = (i == 0) ? nx - 1 : i - 1;
                         if (KIND == XD_STD2D && PRE)
-                            xd_update_std2d_pre<HASB>(sS, cA, cB, c2, c3, sFac, (int)nx, j, i, (int)ip, (int)im, a.q.p[1], a.q.p[2]);
+                            xd_update_std2d_pre<HASB>(sS, cA, cB, c2, c3, sFac, (int)nx, he, j, i, (int)ip, (int)im, a.q.p[1], a.q.p[2]);
                         else if (KIND == XD_STD2D)
                             xd_update_std2d<HASB>(sS, cA, cB, c2, c3, nx, j, i, ip, im, a.q.p[0], a.q.p[1], a.q.p[2], wq, undef);
                         else
@@ -216,7 +227,14 @@ xr_resident_kernel(const XrArgs a)
         }
         // ---- psi back to HBM, state back ----
         double *out = a.S + (i64)b * N;
-        for (i64 p = tid; p < N; p += nth) out[p] = sS[p];
+        if (PRE) {
+            for (int p = tid; p < (int)N; p += nth) {
+                const int j = p / (int)nx, i = p - j * (int)nx;
+                out[p] = sS[j * (int)nx + XD_SPLIT_POS(i, he)];
+            }
+        } else {
+            for (i64 p = tid; p < N; p += nth) out[p] = sS[p];
+        }
         if (tid == 0) {
             st_.omega = om;
             a.st[b] = st_;
