@@ -4,7 +4,7 @@ against the ordering-matched C oracle.
 
 Bar: fields BIT-EXACT (np.array_equal), identical loop counts and overflow flags; flags[1] to 1e-6
 relative (the cluster sums |S| thread -> warp -> cluster in a fixed order, the oracle serially).
-Every cluster size R (1, 2, 4, 8, 16 CTAs) and every run length K (4, 6, 8, 12, 16 cells per thread)
+Every cluster size R (1, 2, 4, 8, 16 CTAs) and every run length K (4, 6, 8, 10, 12, 16 cells per thread)
 is forced through XINV_CLUSTER_R / XINV_CLUSTER_K.
 """
 import numpy as np
@@ -62,7 +62,7 @@ def _force(monkeypatch, R, K):
 
 @pytest.mark.parametrize("bcy,bcx", BCS)
 @pytest.mark.parametrize("R", [1, 2, 4, 8, 16])
-@pytest.mark.parametrize("K", [4, 6, 8, 12, 16])
+@pytest.mark.parametrize("K", [4, 6, 8, 10, 12, 16])
 def test_std2d_cluster_bit_exact(gpu_ctx, monkeypatch, bcy, bcx, R, K):
     """Standard form, every (R, K): ragged nx (a partly filled last run) with fixed-x, nx a multiple of K
     with periodic-x; land cells, whole rows of undef coefficients."""
@@ -120,6 +120,16 @@ def test_cluster_c1_size_to_tolerance_auto(gpu_ctx):
     assert np.array_equal(S_m, S_o) and f_m[2] == f_o[2]
     S_k, f_k = cases.run_std2d(xb, c, "fixed", "periodic", 5000, 1e-8, omega=1.4, check_every=100)
     assert np.array_equal(S_k, S_o) and f_k[2] == f_o[2]
+
+
+def test_cluster_periodic_250_columns_auto(gpu_ctx):
+    """A periodic grid whose width only K = 10 divides (250 columns): engine='auto' still finds a cluster shape."""
+    c = cases.poisson_latlon(100, 250, land=True, noise=1e-6, seed=3)
+    S_o, f_o = cases.run_std2d(oracle, c, "extend", "periodic", 40, -1.0, omega=1.5, ordering="colour")
+    S_g, f_g = cases.run_std2d(xb, c, "extend", "periodic", 40, -1.0, omega=1.5)
+    assert _engine(gpu_ctx) == "cluster"
+    assert np.array_equal(S_g, S_o)
+    _check_flags(f_g, f_o)
 
 
 def test_cluster_land_mask_extend(gpu_ctx):

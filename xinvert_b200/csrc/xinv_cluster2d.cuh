@@ -471,7 +471,7 @@ struct ClusterPlan {
 
 static inline void cluster_plan_release(ClusterPlan &p) { p = ClusterPlan(); }
 
-static const int XC_KS[] = {4, 6, 8, 12, 16};
+static const int XC_KS[] = {4, 6, 8, 10, 12, 16};    // (10: periodic grids of 50, 250, 350 ... columns)
 #define XC_NK ((int)(sizeof(XC_KS) / sizeof(XC_KS[0])))
 
 #define XC_DISPATCH(kind, K, CALL)                       \
@@ -479,12 +479,14 @@ static const int XC_KS[] = {4, 6, 8, 12, 16};
     case 4: CALL(0, 4); break;                           \
     case 6: CALL(0, 6); break;                           \
     case 8: CALL(0, 8); break;                           \
+    case 10: CALL(0, 10); break;                         \
     case 12: CALL(0, 12); break;                         \
     default: CALL(0, 16); break;                         \
     } else switch (K) {                                  \
     case 4: CALL(1, 4); break;                           \
     case 6: CALL(1, 6); break;                           \
     case 8: CALL(1, 8); break;                           \
+    case 10: CALL(1, 10); break;                         \
     case 12: CALL(1, 12); break;                         \
     default: CALL(1, 16); break;                         \
     }
