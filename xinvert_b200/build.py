@@ -59,7 +59,8 @@ def build(force=False, verbose=False):
         if not force and not _stale():           # another process built it while we waited
             return LIB
         tmp = f"{LIB}.tmp.{os.getpid()}"
-        cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
+        extra = os.environ.get("XINV_NVCC_EXTRA", "").split()      # e.g. -DX3_BARRIER_NOINLINE=1 for a synccheck run
+        cmd = [NVCC, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []),
                *[os.path.join(CSRC, s) for s in SOURCES], "-o", tmp, "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:

@@ -135,7 +135,18 @@ __device__ __forceinline__ void x3_mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xf_smem_u32(bar)) : "memory");
 }
 // the compute warps of a CTA meet at named barrier 1 (the producer warp and the spare warp do not take part)
+// Warps whose row is odd and warps whose row is even run different instantiations of x3_march, so they reach the
+// same barrier from different instruction addresses.  PTX allows that (bar.sync is "aligned" within a warp only), but
+// compute-sanitizer's synccheck reports it as "divergent thread(s) in block".  -DX3_BARRIER_NOINLINE=1 puts the barrier
+// behind one function address for the tool (0 reports; 29.5 -> 30.6 us per sweep at 360x180x37, so not the default).
+#ifndef X3_BARRIER_NOINLINE
+#define X3_BARRIER_NOINLINE 0
+#endif
+#if X3_BARRIER_NOINLINE
+__device__ __noinline__ void x3_bar_compute(int nthreads)
+#else
 __device__ __forceinline__ void x3_bar_compute(int nthreads)
+#endif
 {
     asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
