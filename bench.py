@@ -361,6 +361,17 @@ def secondary_configs(ctx, peak, log):
           N3, 1, 200, st, (40.0 if st["row_coeffs"] else 48.0) * N3,
           "one red+black iteration per pass; algorithmic bytes = omega r+w, B, C, F (+ A unless constant along x); "
           "the march is bound by dependent latency per level step (~0.75 us), not by bytes")
+    # the same grid with N2 a profile along the levels (how the reference's notebook 11 forms it): A, B, C and the
+    # factor are one value per row and the kernels read omega and F only
+    c = synthetic.omega_latlon(37, 180, 360, seed=1, n2="1d")
+    p = c["p"]
+    for _ in range(2):
+        S = c["S0"].copy()
+        _, st = xb.solve_standard_3D(S, c["A"], c["B"], c["C"], c["F"], "fixed", "fixed", "periodic", p["del1Sqr"],
+                                     p["ratio2Sqr"], p["ratio1Sqr"], p["optArg"], mxLoop=199, **kw)
+    entry("c3_n2_profile", "configs[2] grid, invert_omega 360x180x37 with N^2 = N^2(p): coefficients constant along x",
+          N3, 1, 200, st, {2: 24.0, 1: 40.0, 0: 48.0}[st["row_coeffs"]] * N3,
+          "row-value kernels: algorithmic bytes = omega r+w, F")
     # c4: invert_GillMatsuno 720x360 beta plane
     c = synthetic.gill_matsuno_beta(360, 720)
     p = c["p"]
@@ -390,8 +401,8 @@ def secondary_configs(ctx, peak, log):
                                      p["ratio2Sqr"], p["ratio1Sqr"], p["optArg"], mxLoop=49, **kw)
     Nn = 300 * 300 * 602
     entry("omega_notebook11", "docs/source/notebooks/11_Omega_equation.ipynb:525-551: invert_omega 601x300x300 "
-          "(the reference: ~730 s per 501-sweep solve)", Nn, 1, 50, st, (40.0 if st["row_coeffs"] else 48.0) * Nn,
-          "HBM-bound: algorithmic bytes = omega r+w, B, C, F (+ A unless constant along x)")
+          "(the reference: ~730 s per 501-sweep solve)", Nn, 1, 50, st, {2: 24.0, 1: 40.0, 0: 48.0}[st["row_coeffs"]] * Nn,
+          "HBM-bound: algorithmic bytes = omega r+w, F (+ B, C unless constant along x, as they are with N^2 = N^2(p))")
     return out
 
 

@@ -115,7 +115,8 @@ typedef struct xinv_stats {
     int64_t dom_launches;     /*               ... and how many launches that covers      */
     int64_t slow_strips;      /* reserved (always 0)                                      */
     int32_t iters_per_pass;   /* fused engine: SOR iterations per pass over HBM (T)       */
-    int32_t row_coeffs;       /* fused engine: 1 = A and C were constant along x (RC kernels) */
+    int32_t row_coeffs;       /* fused engine: 1 = A and C were constant along x (RC kernels; 3-D: A only),
+                                 2 = 3-D with A, B and C all constant along x (row-value kernels) */
 } xinv_stats;
 
 /* ---- context ---------------------------------------------------------- */

@@ -747,6 +747,7 @@ static int problem_begin(xinv_ctx *c, const BeginArgs &a)
     c->stats.engine = pb.cluster.built ? XINV_ENGINE_CLUSTER : pb.engine;
     c->stats.iters_per_pass = (pb.engine == XINV_ENGINE_FUSED && pb.fused.built && !pb.cluster.built) ? pb.fused.T : 1;
     c->stats.row_coeffs = (pb.engine == XINV_ENGINE_FUSED && ((pb.fused.built && pb.fused.rc) || (pb.fused3.built && pb.fused3.arow))) ? 1 : 0;
+    if (pb.engine == XINV_ENGINE_FUSED && pb.fused3.built && pb.fused3.rowsmode) c->stats.row_coeffs = 2;
     pb.open = true;
     return XINV_OK;
 }

@@ -86,20 +86,29 @@ __device__ __forceinline__ double2 x3_ld2(const double *p) { return *reinterpret
 
 // Shared-memory layout of one ring stage (offsets in doubles).  Row r of the omega box is global row
 // y0 - 2 + r; the A, C, Fd, fac and B boxes start one row later (row r <-> y0 - 1 + r).
-template <int TJ, bool AROW>
+// CM = coefficient mode: X3_DENSE (A, B, C, fac as volumes), X3_AROW (A as one value per row), X3_ROWS (A, B, C and
+// fac all as one value per row: the stage holds omega, four vectors of TJ row values and Fd, nothing else).
+#define X3_DENSE 0
+#define X3_AROW 1
+#define X3_ROWS 2
+template <int TJ, int CM>
 struct X3Lay {
     static constexpr int W = X3_W;
     static constexpr int RC = TJ - 2;            // rows of A, C, Fd, fac: everything that is ever updated
     static constexpr int RBN = TJ - 1;           // rows of B: those and the row north of them
     static constexpr int OFF_S = 0;
     static constexpr int OFF_A = TJ * W;
-    static constexpr int A_SZ = AROW ? 32 : RC * W;          // AROW: TJ values (rows y0-2 ...: TMA start coordinates must be even), padded to 128 bytes
+    // row values: TJ per vector (rows y0-2 ...: TMA start coordinates must be even), padded to 128 bytes
+    static constexpr int A_SZ = (CM == X3_ROWS) ? (4 * TJ + 15) / 16 * 16 : (CM == X3_AROW) ? 32 : RC * W;
+    static constexpr int C_SZ = (CM == X3_ROWS) ? 0 : RC * W;
     static constexpr int OFF_C = OFF_A + A_SZ;
-    static constexpr int OFF_FD = OFF_C + RC * W;
+    static constexpr int OFF_FD = OFF_C + C_SZ;
     static constexpr int OFF_FAC = OFF_FD + RC * W;
-    static constexpr int OFF_B = OFF_FAC + RC * W;
-    static constexpr int STAGE = OFF_B + RBN * W;
-    static constexpr uint32_t TX_BYTES = (uint32_t)((TJ * W + (AROW ? TJ : RC * W) + 3 * RC * W + RBN * W) * sizeof(double));
+    static constexpr int OFF_B = OFF_FAC + C_SZ;
+    static constexpr int STAGE = OFF_B + ((CM == X3_ROWS) ? 0 : RBN * W);
+    static constexpr uint32_t TX_BYTES =
+        (uint32_t)(((CM == X3_ROWS) ? TJ * W + 4 * TJ + RC * W
+                                    : TJ * W + ((CM == X3_AROW) ? TJ : RC * W) + 3 * RC * W + RBN * W) * sizeof(double));
     static_assert(TJ <= 32 && (TJ % 2) == 0, "row-value box: at most 256 bytes, a multiple of 16");
 };
 
@@ -155,10 +164,11 @@ __device__ __forceinline__ void x3_bar_compute(int nthreads)
 // loop, kbase even) the colour of the lane's even column is a compile-time constant and the register windows
 // (omega of the last four levels, A of the last three, the operands saved for the black half step) are
 // indexed by constants.
-template <int TJ, int K, bool AROW, bool JODD>
+template <int TJ, int K, int CM, bool JODD>
 __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &nsum, int &ncnt)
 {
-    using L = X3Lay<TJ, AROW>;
+    using L = X3Lay<TJ, CM>;
+    constexpr bool AROW = (CM != X3_DENSE), ROWS = (CM == X3_ROWS);
     constexpr int W = X3_W;
     constexpr int TILE = TJ * W;
     // the coefficient boxes start one row below the omega box: fold the -W into the offsets
@@ -204,15 +214,22 @@ __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &ns
         // ---- red cells of the level of step s-1 (neighbours in y: the staged level, still untouched) ----
         if ((s >= t.s_red0) & (s <= t.s_red1)) {
             const double *r = t.ringrow + prev_off;
-            const double2 Bc = x3_ld2(r + OFF_BC), Bn = x3_ld2(r + OFF_BN), Cc = x3_ld2(r + OFF_C);
-            const double2 Fd = x3_ld2(r + OFF_FD), Fc = x3_ld2(r + OFF_FAC);
+            double2 Bc, Bn, Cc, Fc;
+            if (ROWS) {                                            // one value per row: B of this row and of the row north, C, fac
+                const double *rv = t.arow + prev_off;
+                const double vb = rv[TJ], vn = rv[TJ + 1], vc = rv[2 * TJ], vf = rv[3 * TJ];
+                Bc = make_double2(vb, vb); Bn = make_double2(vn, vn); Cc = make_double2(vc, vc); Fc = make_double2(vf, vf);
+            } else {
+                Bc = x3_ld2(r + OFF_BC); Bn = x3_ld2(r + OFF_BN); Cc = x3_ld2(r + OFF_C); Fc = x3_ld2(r + OFF_FAC);
+            }
+            const double2 Fd = x3_ld2(r + OFF_FD);
             double2 Sn = x3_ld2(r + OFF_S + t.wn), Ss = x3_ld2(r + OFF_S + t.ws);
             if (t.ext_j1 | t.ext_jM) {
                 // the extended boundary row as the cells of rows 1 / ny-2 see it: their own old value
                 if (t.ext_j1) { if (P[U1].x != undef) Ss.x = P[U1].x; if (P[U1].y != undef) Ss.y = P[U1].y; }
                 if (t.ext_jM) { if (P[U1].x != undef) Sn.x = P[U1].x; if (P[U1].y != undef) Sn.y = P[U1].y; }
             }
-            const double Cnext = xm_shfl_down1(Cc.x);              // C of the column east of the pair
+            const double Cnext = ROWS ? Cc.x : xm_shfl_down1(Cc.x);    // C of the column east of the pair
             if (RX) {
                 const double nb = xm_shfl_up1(P[U1].y);
                 P[U1].x = x3_cell(P[U1].x, P[U].x, P[U2].x, Sn.x, Ss.x, P[U1].y, nb, Aw[U].x, Aw[U1].x, Bn.x, Bc.x, Cc.y, Cc.x,
@@ -281,14 +298,15 @@ __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &ns
     }
 }
 
-template <int TJ, int K, int MINB, bool AROW>
+template <int TJ, int K, int MINB, int CM>
 __global__ void __launch_bounds__(TJ * 32, MINB)
 xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant__ CUtensorMap mS1,
                  const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
                  const __grid_constant__ CUtensorMap mC, const __grid_constant__ CUtensorMap mFd,
                  const __grid_constant__ CUtensorMap mFac, const X3Args a)
 {
-    using L = X3Lay<TJ, AROW>;
+    using L = X3Lay<TJ, CM>;
+    constexpr bool AROW = (CM != X3_DENSE), ROWS = (CM == X3_ROWS);
     constexpr int W = X3_W;
     constexpr int TILE = TJ * W;                 // doubles per exchange buffer
     constexpr int STAGE = L::STAGE;
@@ -381,6 +399,11 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
             const int ys = y0 - 2;
             xf_mbar_expect_tx(bar, L::TX_BYTES);
             xf_tma_load_3d(dst + L::OFF_S, mS, bar, bx, ys, b * nz + k);                        // TJ rows
+            if (ROWS) {                          // A, B, C, fac: four vectors of TJ row values in one box
+                xf_tma_load_3d(dst + L::OFF_A, &mA, bar, ys, 0, b * a.cbA * nz + k);
+                xf_tma_load_3d(dst + L::OFF_FD, &mFd, bar, bx, ys + 1, b * a.cbFd * nz + k);
+                return;
+            }
             if (AROW) xf_tma_load_3d(dst + L::OFF_A, &mA, bar, ys, 0, b * a.cbA * nz + k);      // TJ row values (even start)
             else      xf_tma_load_3d(dst + L::OFF_A, &mA, bar, bx, ys + 1, b * a.cbA * nz + k); // TJ-2 rows
             xf_tma_load_3d(dst + L::OFF_C, &mC, bar, bx, ys + 1, b * a.cbC * nz + k);
@@ -403,8 +426,8 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
                 __syncwarp();
             }
         } else if (w < TJ - 1) {
-            if (w & 1) x3_march<TJ, K, AROW, true>(t, rg, nsum, ncnt);
-            else       x3_march<TJ, K, AROW, false>(t, rg, nsum, ncnt);
+            if (w & 1) x3_march<TJ, K, CM, true>(t, rg, nsum, ncnt);
+            else       x3_march<TJ, K, CM, false>(t, rg, nsum, ncnt);
         }
 
         // ---- per-tile norm partial, ticket, loop control by the last tile of the slice ----
@@ -533,7 +556,7 @@ __global__ void x3_pack_derived_kernel(double *__restrict__ Fd, double *__restri
             vf = q.optArg / ((Au + Ac) * ratio2Sqr + (Bn + Bc) * ratio1Sqr + (Ce + Cc));
         }
         Fd[row * pitch + pc] = vF;
-        if (b < nbFac) fac[row * pitch + pc] = vf;
+        if (fac && b < nbFac) fac[row * pitch + pc] = vf;
     }
 }
 
@@ -554,6 +577,28 @@ __global__ void x3_pack_rowvals_kernel(double *__restrict__ vals, const double *
     const i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= rpitch) return;
     for (i64 v = blockIdx.y; v < nv; v += gridDim.y) vals[v * rpitch + j] = (j < ny) ? A[(v * ny + j) * nx] : 0.0;
+}
+
+// X3_ROWS operand: vals[v][0..3][j] = A, B, C and the factor of row j of (volume x level) v, from column 0 of the
+// dense arrays (which x3_rowconst_kernel has found constant along x); the factor with the operations of numbas.py:166-168
+__global__ void x3_pack_rows4_kernel(double *__restrict__ vals, XdCoef q, i64 nz, i64 ny, i64 nx, i64 rpitch, i64 nb)
+{
+    const i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rpitch) return;
+    const double ratio2Sqr = q.p[1], ratio1Sqr = q.p[2];
+    for (i64 v = blockIdx.y; v < nz * nb; v += gridDim.y) {
+        const i64 b = v / nz, k = v - b * nz;
+        double va = 0.0, vb = 0.0, vc = 0.0, vf = 0.0;
+        if (j < ny) {
+            const double *A = q.c[0] + b * q.cs[0], *B = q.c[1] + b * q.cs[1], *C = q.c[2] + b * q.cs[2];
+            const i64 o = (k * ny + j) * nx;
+            va = A[o]; vb = B[o]; vc = C[o];
+            if ((k >= 1) && (k <= nz - 2) && (j >= 1) && (j <= ny - 2))
+                vf = q.optArg / ((A[o + ny * nx] + va) * ratio2Sqr + (B[o + nx] + vb) * ratio1Sqr + (vc + vc));
+        }
+        double *d = vals + v * 4 * rpitch + j;
+        d[0] = va; d[rpitch] = vb; d[2 * rpitch] = vc; d[3 * rpitch] = vf;
+    }
 }
 
 __global__ void x3_unpack_kernel(double *__restrict__ dst, const double *__restrict__ buf0,
@@ -661,7 +706,33 @@ __global__ void x3_front_derived_kernel(double *__restrict__ Fd, double *__restr
             vf = optArg / ((Au + Ac) * ratio2Sqr + (Bn + Bc) * ratio1Sqr + (Ce + Cc));
         }
         Fd[row * pitch + pc] = vF;
-        if (b < nbFac) fac[row * pitch + pc] = vf;
+        if (fac && b < nbFac) fac[row * pitch + pc] = vf;
+    }
+}
+
+// X3_ROWS operand of the front end (N2 without a column axis): the same values x3_front_bc_kernel and
+// x3_front_derived_kernel form cell by cell, once per row
+__global__ void x3_front_rows4_kernel(double *__restrict__ vals, const double *__restrict__ rows, const double *__restrict__ N2,
+                                      i64 s0, i64 s1, i64 s2, i64 nz, i64 ny, i64 rpitch, i64 nb, double ratio2Sqr,
+                                      double ratio1Sqr, double optArg)
+{
+    const i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rpitch) return;
+    for (i64 v = blockIdx.y; v < nz * nb; v += gridDim.y) {
+        const i64 b = v / nz, k = v - b * nz;
+        double va = 0.0, vb = 0.0, vc = 0.0, vf = 0.0;
+        if (j < ny) {
+            const double *n2 = N2 + b * s0 + k * s1;
+            va = rows[j];
+            vb = n2[j * s2] * rows[ny + j];
+            vc = n2[j * s2] / rows[2 * ny + j];
+            if ((k >= 1) && (k <= nz - 2) && (j >= 1) && (j <= ny - 2)) {
+                const double Bn = n2[(j + 1) * s2] * rows[ny + j + 1];
+                vf = optArg / ((va + va) * ratio2Sqr + (Bn + vb) * ratio1Sqr + (vc + vc));
+            }
+        }
+        double *d = vals + v * 4 * rpitch + j;
+        d[0] = va; d[rpitch] = vb; d[2 * rpitch] = vc; d[3 * rpitch] = vf;
     }
 }
 
@@ -717,6 +788,8 @@ struct Fused3Plan {
     X3Front front;
     int variant = 0;
     bool arow = false;             // A constant along x: AROW kernels
+    bool rowsmode = false;         // ... and so are B and C: X3_ROWS kernels (A, B, C, fac as row values)
+    int cm() const { return rowsmode ? X3_ROWS : arow ? X3_AROW : X3_DENSE; }
     bool coop = false;
     int ppl = 1;
     unsigned long long gbar_base = 0;
@@ -740,21 +813,21 @@ static inline bool fused3_plan_supported(const XdGeom &g, std::string &why)
     return true;
 }
 
-template <int TJ, int K, bool AROW>
+template <int TJ, int K, int CM>
 static size_t x3_smem_bytes()
 {
-    const size_t stage = (size_t)X3Lay<TJ, AROW>::STAGE * sizeof(double);
+    const size_t stage = (size_t)X3Lay<TJ, CM>::STAGE * sizeof(double);
     return (size_t)K * stage + (size_t)2 * TJ * X3_W * sizeof(double) + (size_t)TJ * 16 + (size_t)K * 16 + 16;
 }
-template <int TJ, int K, int MINB, bool AROW>
+template <int TJ, int K, int MINB, int CM>
 static cudaError_t x3_prepare(size_t *smem, int *blocks_per_sm)
 {
-    *smem = x3_smem_bytes<TJ, K, AROW>();
-    cudaError_t e = cudaFuncSetAttribute(xm3_std3d_kernel<TJ, K, MINB, AROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+    *smem = x3_smem_bytes<TJ, K, CM>();
+    cudaError_t e = cudaFuncSetAttribute(xm3_std3d_kernel<TJ, K, MINB, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, xm3_std3d_kernel<TJ, K, MINB, AROW>, TJ * 32, *smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, xm3_std3d_kernel<TJ, K, MINB, CM>, TJ * 32, *smem);
 }
-template <int TJ, int K, int MINB, bool AROW>
+template <int TJ, int K, int MINB, int CM>
 static cudaError_t x3_launch(const Fused3Plan &p, cudaStream_t stream)
 {
     cudaLaunchConfig_t cfg = {};
@@ -767,7 +840,7 @@ static cudaError_t x3_launch(const Fused3Plan &p, cudaStream_t stream)
     attr[0].val.cooperative = (p.args.npass > 1) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, xm3_std3d_kernel<TJ, K, MINB, AROW>, p.mS[0], p.mS[1], p.mA, p.mB, p.mC, p.mFd, p.mFac, p.args);
+    return cudaLaunchKernelEx(&cfg, xm3_std3d_kernel<TJ, K, MINB, CM>, p.mS[0], p.mS[1], p.mA, p.mB, p.mC, p.mFd, p.mFac, p.args);
 }
 
 #define X3_DISPATCH1(v, AR, CALL)                     \
@@ -785,7 +858,10 @@ static cudaError_t x3_launch(const Fused3Plan &p, cudaStream_t stream)
     case 10: CALL(20, 3, 1, AR); break;               \
     default: CALL(24, 2, 1, AR); break;               \
     }
-#define X3_DISPATCH(v, arow, CALL) if (arow) { X3_DISPATCH1(v, true, CALL) } else { X3_DISPATCH1(v, false, CALL) }
+#define X3_DISPATCH(v, cm, CALL)                                              \
+    if ((cm) == X3_ROWS) { X3_DISPATCH1(v, X3_ROWS, CALL) }                    \
+    else if ((cm) == X3_AROW) { X3_DISPATCH1(v, X3_AROW, CALL) }               \
+    else { X3_DISPATCH1(v, X3_DENSE, CALL) }
 
 // Tile shape.  Measured on B200 (37 x 180 x 360 and 300 x 300 x 602 volumes): a step of the march costs about
 // 0.83 us with 16-row tiles (ring of 4), 0.72 us with 12-row tiles (ring of 5) and 0.78 us with two co-resident
@@ -807,6 +883,36 @@ static void x3_choose(i64 nz, i64 ny, i64 nx, i64 batch, int sm_count, int *vari
         const double rounds = (tiles <= slots) ? 1.0 : (double)tiles / slots;
         const double cost = rounds * ((double)nz + 5.0) * t_step[ci];
         if (cost < best - 1e-9) { best = cost; *variant = cand[ci]; }
+    }
+}
+
+// Row-value kernels (X3_ROWS): a step costs 0.63 us with 16-row tiles, 0.54 us with 12-row tiles, 0.85 us with 20-row
+// tiles, plus about 2.7 us per pass (measured at 37 x 180 x 360 and 300 x 300 x 602); tiles are dealt round-robin, so
+// the rounds are whole; with omega and F as the only volumes the halo levels of a level range are cheap, and splitting
+// the levels in two pays when it brings the tiles of a small volume to one round of the machine
+// (37 x 180 x 360: 24.6 -> 21.6 us per sweep).
+static void x3_choose_rows(i64 nz, i64 ny, i64 nx, i64 batch, int sm_count, int *variant, int *ntz)
+{
+    const i64 ntx = (nx + X3_W - 5) / (X3_W - 4);
+    static const int cand[] = {6, 0, 10};
+    static const double t_step[] = {0.54, 0.63, 0.85};
+    double best = 1e300;
+    *variant = 6; *ntz = 1;
+    for (int nt = 1; nt <= 2; ++nt) {
+        i64 ZB = (nz + nt - 1) / nt;
+        ZB += (ZB & 1);
+        if (nt > 1 && ZB < 8) continue;
+        const i64 nzt = (nz + ZB - 1) / ZB;
+        const double steps = (nzt == 1) ? (double)nz + 2.0 : (double)ZB + 2.0;
+        for (int ci = 0; ci < 3; ++ci) {
+            const X3Variant v = X3_VARIANTS[cand[ci]];
+            const int RB = v.TJ - 4;
+            const i64 tiles = ntx * ((ny + RB - 1) / RB) * nzt * batch;
+            const i64 slots = (i64)sm_count * v.MINB;
+            const double rounds = (double)((tiles + slots - 1) / slots);
+            const double cost = rounds * steps * t_step[ci] + 2.7;
+            if (cost < best * 0.98) { best = cost; *variant = cand[ci]; *ntz = nt; }
+        }
     }
 }
 
@@ -863,18 +969,38 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
             }
             p.arow = (h == 0);
         }
+        // ---- ... and B and C too?  (front end: N2 without a column axis; XINV_FUSED3_ROWS=0 switches the mode off) ----
+        const char *er = getenv("XINV_FUSED3_ROWS");
+        p.rowsmode = p.arow && !(er && atoi(er) == 0);
+        if (fe) {
+            p.rowsmode = p.rowsmode && (p.front.ns[3] == 0);
+        } else if (p.rowsmode) {
+            const i64 nrB = rows * (cb[1] ? batch : 1), nrC = rows * (cb[2] ? batch : 1);
+            x3_rowconst_kernel<<<gridfor(nx, nrB), blk, 0, stream>>>(q.c[1], nrB, nx, (int *)flag);
+            x3_rowconst_kernel<<<gridfor(nx, nrC), blk, 0, stream>>>(q.c[2], nrC, nx, (int *)flag);
+            int h = 1;
+            if ((e = cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+                (e = cudaStreamSynchronize(stream)) != cudaSuccess) {
+                why = std::string("row-constancy check: ") + cudaGetErrorString(e);
+                fused3_plan_release(p);
+                return -1;
+            }
+            p.rowsmode = (h == 0);
+        }
     }
+    const bool rm = p.rowsmode;
     const i64 rpitch = (ny + 1) / 2 * 2;         // row-value vectors: TMA strides are multiples of 16 bytes
-    const i64 nvA = nz * (cb[0] ? batch : 1);    // (volume x level) planes of A
-    X3_ALLOC(p.bufA, 2, p.arow ? (size_t)nvA * rpitch * sizeof(double) : vol_bytes * (cb[0] ? batch : 1));
-    X3_ALLOC(p.bufC, 3, vol_bytes * (cb[2] ? batch : 1));
+    const i64 nvA = nz * ((rm ? cbFac : cb[0]) ? batch : 1);    // (volume x level) planes of A (X3_ROWS: of A, B, C, fac)
+    X3_ALLOC(p.bufA, 2, p.arow ? (size_t)nvA * (rm ? 4 : 1) * rpitch * sizeof(double) : vol_bytes * (cb[0] ? batch : 1));
+    X3_ALLOC(p.bufC, 3, rm ? 16 : vol_bytes * (cb[2] ? batch : 1));
     X3_ALLOC(p.bufFd, 4, vol_bytes * (cbFd ? batch : 1));
-    X3_ALLOC(p.bufFac, 5, vol_bytes * (cbFac ? batch : 1));
-    X3_ALLOC(p.bufB, 6, vol_bytes * (cb[1] ? batch : 1));
+    X3_ALLOC(p.bufFac, 5, rm ? 16 : vol_bytes * (cbFac ? batch : 1));
+    X3_ALLOC(p.bufB, 6, rm ? 16 : vol_bytes * (cb[1] ? batch : 1));
 #undef X3_ALLOC
     int ntz = 1;
     {
-        x3_choose(nz, ny, nx, batch, sm_count, &p.variant, &ntz);
+        if (rm) x3_choose_rows(nz, ny, nx, batch, sm_count, &p.variant, &ntz);
+        else    x3_choose(nz, ny, nx, batch, sm_count, &p.variant, &ntz);
         const char *env = getenv("XINV_FUSED3_VARIANT");
         if (env) { p.variant = atoi(env); ntz = 1; }
         if (p.variant < 0 || p.variant >= X3_NVARIANTS) p.variant = 0;
@@ -889,22 +1015,31 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
         const X3Front &f = p.front;
         cudaMemsetAsync(p.bufS[0], 0, vol_bytes * batch, stream);      // zero initial guess (apps.py:2145), ghosts included
         cudaMemsetAsync(p.bufS[1], 0, vol_bytes * batch, stream);
-        x3_front_rowvals_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, f.rows, nvA, ny, rpitch);
-        x3_front_bc_kernel<<<gridfor(pitch, rows * (feb ? batch : 1)), blk, 0, stream>>>(
-            (double *)p.bufB, (double *)p.bufC, f.rows, f.N2, f.ns[0], f.ns[1], f.ns[2], f.ns[3], nz, ny, nx, pitch,
-            feb ? batch : 1, periodic);
+        if (rm) {
+            x3_front_rows4_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, f.rows, f.N2, f.ns[0], f.ns[1], f.ns[2],
+                                                                            nz, ny, rpitch, feb ? batch : 1, q.p[1], q.p[2], q.optArg);
+        } else {
+            x3_front_rowvals_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, f.rows, nvA, ny, rpitch);
+            x3_front_bc_kernel<<<gridfor(pitch, rows * (feb ? batch : 1)), blk, 0, stream>>>(
+                (double *)p.bufB, (double *)p.bufC, f.rows, f.N2, f.ns[0], f.ns[1], f.ns[2], f.ns[3], nz, ny, nx, pitch,
+                feb ? batch : 1, periodic);
+        }
         x3_front_derived_kernel<<<gridfor(pitch, rows * batch), blk, 0, stream>>>(
-            (double *)p.bufFd, (double *)p.bufFac, f.rows, f.N2, f.ns[0], f.ns[1], f.ns[2], f.ns[3], f.F, nz, ny, nx, pitch,
+            (double *)p.bufFd, rm ? nullptr : (double *)p.bufFac, f.rows, f.N2, f.ns[0], f.ns[1], f.ns[2], f.ns[3], f.F, nz, ny, nx, pitch,
             batch, feb ? batch : 1, periodic, f.user_undef, q.undef, q.p[0], q.p[1], q.p[2], q.optArg, (int *)flag);
     } else {
         pack(p.bufS[0], dS, g.N, batch);
         pack(p.bufS[1], dS, g.N, batch);   // levels 0 / nz-1 and all pad columns of both buffers start identical
-        if (p.arow) x3_pack_rowvals_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, q.c[0], nvA, ny, nx, rpitch);
-        else        pack(p.bufA, q.c[0], q.cs[0], cb[0] ? batch : 1);
-        pack(p.bufB, q.c[1], q.cs[1], cb[1] ? batch : 1);
-        pack(p.bufC, q.c[2], q.cs[2], cb[2] ? batch : 1);
+        if (rm) {
+            x3_pack_rows4_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, q, nz, ny, nx, rpitch, cbFac ? batch : 1);
+        } else {
+            if (p.arow) x3_pack_rowvals_kernel<<<gridfor(rpitch, nvA), blk, 0, stream>>>((double *)p.bufA, q.c[0], nvA, ny, nx, rpitch);
+            else        pack(p.bufA, q.c[0], q.cs[0], cb[0] ? batch : 1);
+            pack(p.bufB, q.c[1], q.cs[1], cb[1] ? batch : 1);
+            pack(p.bufC, q.c[2], q.cs[2], cb[2] ? batch : 1);
+        }
         x3_pack_derived_kernel<<<gridfor(pitch, rows * (cbFd ? batch : 1)), blk, 0, stream>>>(
-            (double *)p.bufFd, (double *)p.bufFac, q, nz, ny, nx, pitch, cbFd ? batch : 1, cbFac ? batch : 1, periodic);
+            (double *)p.bufFd, rm ? nullptr : (double *)p.bufFac, q, nz, ny, nx, pitch, cbFd ? batch : 1, cbFac ? batch : 1, periodic);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) {
         why = std::string("pack kernels: ") + cudaGetErrorString(e);
@@ -914,15 +1049,16 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
     // tensor maps: (pitch, ny, levels x volumes); boxes 64 columns x TJ rows (omega), TJ-1 (B), TJ-2 (A, C, Fd, fac)
     if (xf_make_map(&p.mS[0], p.bufS[0], pitch, ny, nz * batch, X3_W, v.TJ, why) ||
         xf_make_map(&p.mS[1], p.bufS[1], pitch, ny, nz * batch, X3_W, v.TJ, why) ||
-        (p.arow ? xf_make_row_map(&p.mA, p.bufA, ny, rpitch, nvA, v.TJ, 1, why)
+        (p.arow ? xf_make_row_map(&p.mA, p.bufA, ny, rpitch, nvA, v.TJ, rm ? 4 : 1, why)
                 : xf_make_map(&p.mA, p.bufA, pitch, ny, nvA, X3_W, v.TJ - 2, why)) ||
-        xf_make_map(&p.mB, p.bufB, pitch, ny, nz * (cb[1] ? batch : 1), X3_W, v.TJ - 1, why) ||
-        xf_make_map(&p.mC, p.bufC, pitch, ny, nz * (cb[2] ? batch : 1), X3_W, v.TJ - 2, why) ||
         xf_make_map(&p.mFd, p.bufFd, pitch, ny, nz * (cbFd ? batch : 1), X3_W, v.TJ - 2, why) ||
-        xf_make_map(&p.mFac, p.bufFac, pitch, ny, nz * (cbFac ? batch : 1), X3_W, v.TJ - 2, why)) {
+        (!rm && (xf_make_map(&p.mB, p.bufB, pitch, ny, nz * (cb[1] ? batch : 1), X3_W, v.TJ - 1, why) ||
+                 xf_make_map(&p.mC, p.bufC, pitch, ny, nz * (cb[2] ? batch : 1), X3_W, v.TJ - 2, why) ||
+                 xf_make_map(&p.mFac, p.bufFac, pitch, ny, nz * (cbFac ? batch : 1), X3_W, v.TJ - 2, why)))) {
         fused3_plan_release(p);
         return -1;
     }
+    if (rm) p.mB = p.mC = p.mFac = p.mFd;        // unused by the X3_ROWS kernels
     X3Args &a = p.args;
     a.Sbuf[0] = (double *)p.bufS[0];
     a.Sbuf[1] = (double *)p.bufS[1];
@@ -938,14 +1074,14 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
     a.ntz = (int)((nz + a.ZB - 1) / a.ZB);
     a.batch = (int)batch;
     a.bcy = g.bcy; a.bcx = g.bcx;
-    a.cbA = cb[0]; a.cbB = cb[1]; a.cbC = cb[2]; a.cbFd = cbFd; a.cbFac = cbFac;
+    a.cbA = rm ? cbFac : cb[0]; a.cbB = cb[1]; a.cbC = cb[2]; a.cbFd = cbFd; a.cbFac = cbFac;
     a.r2 = q.p[1]; a.r1 = q.p[2]; a.undef = q.undef;
     p.batch = batch;
     p.nblk_partials = a.ntx * a.nty * a.ntz;
     const i64 tiles = (i64)a.ntx * a.nty * a.ntz * batch;
     int blocks_per_sm = 0;
 #define X3_PREP(TJ_, K_, MB_, AR_) e = x3_prepare<TJ_, K_, MB_, AR_>(&p.smem, &blocks_per_sm)
-    X3_DISPATCH(p.variant, p.arow, X3_PREP);
+    X3_DISPATCH(p.variant, p.cm(), X3_PREP);
 #undef X3_PREP
     if (e != cudaSuccess || blocks_per_sm < 1) {
         why = std::string("3-D fused kernel does not fit: ") + cudaGetErrorString(e);
@@ -987,7 +1123,7 @@ static inline int fused3_sweep(Fused3Plan &p, cudaStream_t stream, XdSliceState 
     if (npass > 1) {
         a.npass = npass;
         a.gbar_base = p.gbar_base;
-        X3_DISPATCH(p.variant, p.arow, X3_GO);
+        X3_DISPATCH(p.variant, p.cm(), X3_GO);
         if (e == cudaSuccess) {
             p.gbar_base += (unsigned long long)p.grid * (unsigned long long)(npass - 1);
             *launches += 1;
@@ -1000,7 +1136,7 @@ static inline int fused3_sweep(Fused3Plan &p, cudaStream_t stream, XdSliceState 
     a.npass = 1;
     a.gbar_base = p.gbar_base;
     for (int n = 0; n < npass; ++n) {
-        X3_DISPATCH(p.variant, p.arow, X3_GO);
+        X3_DISPATCH(p.variant, p.cm(), X3_GO);
         if (e != cudaSuccess) return -1;
         *launches += 1;
     }
