@@ -187,14 +187,17 @@ __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &ns
     int prev_stage = -1;                             // ... and its stage (-1: none to hand back)
     const int lane = threadIdx.x & 31;
 
-    auto step = [&](auto u_tag, const int s) {
+    // ST ("steady"): a step in which a level arrives, red, black and a finished level all take place and the level
+    // is one of 1 .. nz-2: every range test below is true at compile time (most steps of a march)
+    auto step = [&](auto u_tag, auto st_tag, const int s) {
         constexpr int U = decltype(u_tag)::value;    // s & 3
+        constexpr bool ST = decltype(st_tag)::value;
         constexpr int U1 = (U + 3) & 3, U2 = (U + 2) & 3, U3 = (U + 1) & 3;   // slots of the levels of steps s-1, s-2, s-3
         // red cell of the level of step s-1 = the even column of the pair  <=>  j + kbase + s - 1 even
         constexpr bool RX = ((int(JODD) + U + 1) & 1) == 0;
         int cur_off = prev_off, cur_stage = -1;
         // ---- a level arrives ----
-        if (s < t.s_load) {
+        if (ST || (s < t.s_load)) {
             xf_mbar_wait(&t.bars[rg.cons], (rg.phase >> rg.cons) & 1u);
             rg.phase ^= (1u << rg.cons);
             cur_off = rg.cons * STAGE;
@@ -204,7 +207,7 @@ __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &ns
             P[U] = x3_ld2(g + OFF_S);
             if (AROW) { const double av = t.arow[cur_off]; Aw[U] = make_double2(av, av); }
             else      Aw[U] = x3_ld2(g + OFF_A);
-            if ((t.ext_j0 | t.ext_jN) & (s >= t.s_ext0) & (s <= t.s_ext1)) {   // numbas.py:87-115: levels 1..nz-2 only
+            if ((t.ext_j0 | t.ext_jN) && (ST || ((s >= t.s_ext0) & (s <= t.s_ext1)))) {   // numbas.py:87-115: levels 1..nz-2 only
                 if (t.ext_j0) P[U] = xm_extend(P[U], x3_ld2(g + OFF_S + W), t.gx, t.nx, t.periodic, undef);
                 else          P[U] = xm_extend(P[U], x3_ld2(g + OFF_S - W), t.gx, t.nx, t.periodic, undef);
             }
@@ -212,7 +215,7 @@ __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &ns
             P[U] = zero2; Aw[U] = zero2;
         }
         // ---- red cells of the level of step s-1 (neighbours in y: the staged level, still untouched) ----
-        if ((s >= t.s_red0) & (s <= t.s_red1)) {
+        if (ST || ((s >= t.s_red0) & (s <= t.s_red1))) {
             const double *r = t.ringrow + prev_off;
             double2 Bc, Bn, Cc, Fc;
             if (ROWS) {                                            // one value per row: B of this row and of the row north, C, fac
@@ -247,7 +250,7 @@ __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &ns
         // publish the row (red cells final for this iteration) for the black half step of the next step
         *reinterpret_cast<double2 *>(t.xrow + (U & 1) * TILE) = P[U1];
         // ---- black cells of the level of step s-2 (neighbours in y: rows published in the previous step) ----
-        const bool blk = (s >= t.s_blk0) & (s <= t.s_blk1);
+        const bool blk = ST || ((s >= t.s_blk0) & (s <= t.s_blk1));
         if (blk) {
             constexpr int Q = (U + 1) & 1;                         // slot written in the previous step
             const double *xr = t.xrow + Q * TILE;
@@ -263,7 +266,7 @@ __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &ns
             }
         }
         // ---- an owned level is complete: norm over owned cells (numbas.py:1689-1708), store ----
-        if ((s >= t.s_fin0) & (s <= t.s_fin1)) {
+        if (ST || ((s >= t.s_fin0) & (s <= t.s_fin1))) {
             xm_norm_acc_lane(nsum, ncnt, P[U2].x, t.own_x, undef);
             xm_norm_acc_lane(nsum, ncnt, P[U2].y, t.own_y, undef);
             if (blk) {                                             // levels 0 and nz-1 never change
@@ -277,7 +280,7 @@ __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &ns
         }
         outp += t.plane;
         // the stage of the previous step's level has been read for the last time: hand it back to the producer
-        if (prev_stage >= 0) {
+        if (ST || prev_stage >= 0) {
             __syncwarp();
             if (lane == 0) x3_mbar_arrive(&t.bars[K + prev_stage]);
         }
@@ -286,11 +289,21 @@ __device__ __forceinline__ void x3_march(const X3Tile &t, X3Ring &rg, double &ns
         x3_bar_compute((TJ - 2) * 32);           // rows published
     };
 
+    // steady steps [lo, hi]: groups of four steps inside that range run without the range tests
+    const int lo = max(max(max(1, t.s_red0), max(t.s_blk0, t.s_fin0)), t.s_ext0);
+    const int hi = min(min(min(t.s_load - 1, t.s_red1), min(t.s_blk1, t.s_fin1)), t.s_ext1);
     for (int s0 = 0; s0 < t.nsteps; s0 += 4) {
-        step(std::integral_constant<int, 0>{}, s0);
-        if (s0 + 1 < t.nsteps) step(std::integral_constant<int, 1>{}, s0 + 1);
-        if (s0 + 2 < t.nsteps) step(std::integral_constant<int, 2>{}, s0 + 2);
-        if (s0 + 3 < t.nsteps) step(std::integral_constant<int, 3>{}, s0 + 3);
+        if ((s0 >= lo) & (s0 + 3 <= hi)) {
+            step(std::integral_constant<int, 0>{}, std::true_type{}, s0);
+            step(std::integral_constant<int, 1>{}, std::true_type{}, s0 + 1);
+            step(std::integral_constant<int, 2>{}, std::true_type{}, s0 + 2);
+            step(std::integral_constant<int, 3>{}, std::true_type{}, s0 + 3);
+        } else {
+            step(std::integral_constant<int, 0>{}, std::false_type{}, s0);
+            if (s0 + 1 < t.nsteps) step(std::integral_constant<int, 1>{}, std::false_type{}, s0 + 1);
+            if (s0 + 2 < t.nsteps) step(std::integral_constant<int, 2>{}, std::false_type{}, s0 + 2);
+            if (s0 + 3 < t.nsteps) step(std::integral_constant<int, 3>{}, std::false_type{}, s0 + 3);
+        }
     }
     if (prev_stage >= 0) {                           // a level that arrived in the very last step
         __syncwarp();
