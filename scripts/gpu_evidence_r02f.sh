@@ -1,8 +1,8 @@
 #!/bin/bash
-# Round-2 evidence for the final code (after the CTA-level combine of the norm partials in the 2-D marching kernel):
+# Round-2 evidence for the final code (CTA-level combine of the norm partials + replicated loop control in the 2-D marching kernel):
 # smoke, the whole GPU suite, reference arm, the default bench line, C5 / C1 lines, launch list, ncu --set full of the RC
-# marching kernel and of the 3-D kernels.      gpurun --timeout 1800 -- 'bash scripts/gpu_evidence_r02e.sh <tag>'
-TAG=${1:-r02e}
+# marching kernel and of the 3-D kernels.      gpurun --timeout 1800 -- 'bash scripts/gpu_evidence_r02f.sh <tag>'
+TAG=${1:-r02f}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1

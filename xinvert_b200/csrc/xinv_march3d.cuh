@@ -331,6 +331,7 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
     i64 *red_cnt = reinterpret_cast<i64 *>(red_sum + TJ);   // [TJ]
     uint64_t *bars = reinterpret_cast<uint64_t *>(red_cnt + TJ);   // [2 K]: landed | free
     int *box = reinterpret_cast<int *>(bars + 2 * K);        // [4] CTA-wide broadcasts
+    XdSliceState *lst = reinterpret_cast<XdSliceState *>(box + 4);   // replicated loop control: this CTA's copy of its slice's state
 
     const int lane = threadIdx.x & 31;
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // tile row of this warp (warp-uniform)
@@ -349,6 +350,11 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
     const int tpl = a.ntx * a.nty;               // tiles per level range
     const int tps = tpl * a.ntz;                 // tiles per slice
     const int total = tps * a.batch;
+    // Replicated loop control (every CTA has at most one tile per pass, several passes per launch; cf. xinv_march2d.cuh):
+    // no CTA sums the partials and runs numbas.py:197-210 BEFORE the grid barrier; behind it warp 0 of every CTA does
+    // so for its own slice, from the same partials in the same order, on a copy of the slice's state kept in shared
+    // memory for the whole launch; the CTA with the slice's first tile writes the state back for the host.
+    const bool repl = (total <= (int)gridDim.x) && a.npass > 1;
     X3Ring rg;
     rg.cons = 0;
     rg.phase = (w == 0) ? 0xffffffffu : 0u;      // producer: a fresh "free" barrier counts as completed (parity 1)
@@ -361,7 +367,14 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
         const int yb = trem / a.ntx, xb = trem - yb * a.ntx;
         // slice state: constant while any tile of the slice is still to do in this pass
         // (read through L2: another SM rewrites it between two passes of one launch)
-        if (threadIdx.x == 0) { box[0] = __ldcg(&a.st[b].active); box[1] = __ldcg(&a.st[b].cur); }
+        if (threadIdx.x == 0) {
+            if (repl) {
+                if (pp == 0) *lst = a.st[b];     // (global state: first pass of the launch only)
+                box[0] = lst->active; box[1] = lst->cur;
+            } else {
+                box[0] = __ldcg(&a.st[b].active); box[1] = __ldcg(&a.st[b].cur);
+            }
+        }
         __syncthreads();
         const int active = box[0], cur = box[1];
         __syncthreads();                         // box is rewritten by the next tile
@@ -456,11 +469,16 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
             i64 tc = 0;
             #pragma unroll
             for (int r = 0; r < TJ; ++r) { ts += red_sum[r]; tc += red_cnt[r]; }
-            a.psum[(i64)b * tps + tidx] = ts;
-            a.pcnt[(i64)b * tps + tidx] = tc;
-            __threadfence();
-            const unsigned tk = atomicAdd(&a.ticket[b], 1u);
-            box[2] = (tk == (unsigned)tps - 1u);
+            // (replicated loop control: two sets of slots by the parity of the pass, published by the grid barrier)
+            const i64 slot = (repl ? (i64)(pp & 1) * a.batch * tps : 0) + (i64)b * tps + tidx;
+            a.psum[slot] = ts;
+            a.pcnt[slot] = tc;
+            box[2] = 0;
+            if (!repl) {
+                __threadfence();
+                const unsigned tk = atomicAdd(&a.ticket[b], 1u);
+                box[2] = (tk == (unsigned)tps - 1u);
+            }
         }
         __syncthreads();
         const int last = box[2];
@@ -491,7 +509,7 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
         __syncthreads();                         // box[2] / reduction scratch are rewritten by the next tile
     }
     // ---- grid-wide barrier before the next pass of this launch (cooperative launch) ----
-    if (pp + 1 < a.npass) {
+    if (pp + 1 < a.npass || repl) {              // (replicated loop control: also behind the last pass of the launch)
         __syncthreads();
         int go_on = 1;
         if (threadIdx.x == 0) {
@@ -502,12 +520,61 @@ xm3_std3d_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant_
             do {
                 asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.gbar) : "memory");
             } while (seen < want);
-            int na;
-            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(na) : "l"(a.nactive) : "memory");
-            go_on = (na != 0);
-            if (!go_on && pp + 2 < a.npass) atomicAdd(a.gbar, (unsigned long long)(a.npass - 2 - pp));
+            if (!repl || a.batch > 1) {          // (replicated: read before this boundary's verdicts lower it -- a stale
+                int na;                          // count only delays the exit by a pass; a single slice needs no count)
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(na) : "l"(a.nactive) : "memory");
+                go_on = (na != 0);
+                if (!repl && !go_on && pp + 2 < a.npass) atomicAdd(a.gbar, (unsigned long long)(a.npass - 2 - pp));
+            }
         }
-        go_on = __syncthreads_or(go_on && threadIdx.x == 0);
+        if (repl) {
+            __syncthreads();                     // the barrier has been passed: known to every warp
+            const int tile0 = blockIdx.x;
+            if (w == 0 && tile0 < total && __shfl_sync(0xffffffffu, lst->active, 0)) {   // the CTA's slice ran in this pass
+                const int b = tile0 / tps;
+                const i64 poff = (i64)(pp & 1) * a.batch * tps + (i64)b * tps;
+                // fixed assignment of partials to lanes and a fixed shuffle tree, loads of eight steps in flight
+                double s_ = 0.0;
+                i64 c_ = 0;
+                for (int p0 = lane; p0 < tps; p0 += 32 * 8) {
+                    double vs[8];
+                    i64 vc[8];
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const int p = p0 + 32 * m;
+                        vs[m] = (p < tps) ? __ldcg(a.psum + poff + p) : 0.0;
+                        vc[m] = (p < tps) ? __ldcg(a.pcnt + poff + p) : 0;
+                    }
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        if (p0 + 32 * m < tps) { s_ += vs[m]; c_ += vc[m]; }
+                    }
+                }
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s_ += __shfl_down_sync(0xffffffffu, s_, o);
+                    c_ += __shfl_down_sync(0xffffffffu, c_, o);
+                }
+                if (lane == 0) {
+                    XdSliceState st_ = *lst;
+                    xd_decide(st_, s_, c_, a.tol, a.mxLoop, 0);       // no norm == 0 exit in 3-D (numbas.py:206)
+                    st_.cur ^= 1;
+                    *lst = st_;
+                    if (tile0 == b * tps) {      // the CTA with the slice's first tile keeps the global copy current
+                        a.st[b] = st_;
+                        if (!st_.active) atomicSub(a.nactive, 1);
+                    }
+                }
+            }
+            __syncthreads();                     // the verdict is known to every warp of the CTA
+            // one slice: every CTA knows the verdict; several: all CTAs leave at the same boundary (monotonic arrival
+            // counter), so they go by the count of active slices
+            if (a.batch == 1) go_on = (tile0 < total) && lst->active;
+            go_on = __syncthreads_or((a.batch == 1) ? (go_on && threadIdx.x == 0) : (go_on && threadIdx.x == 0));
+            if (!go_on && threadIdx.x == 0 && pp + 1 < a.npass) atomicAdd(a.gbar, (unsigned long long)(a.npass - 1 - pp));
+        } else {
+            go_on = __syncthreads_or(go_on && threadIdx.x == 0);
+        }
         if (!go_on) break;
         asm volatile("fence.proxy.async.global;" ::: "memory");
     }
@@ -830,7 +897,7 @@ template <int TJ, int K, int CM>
 static size_t x3_smem_bytes()
 {
     const size_t stage = (size_t)X3Lay<TJ, CM>::STAGE * sizeof(double);
-    return (size_t)K * stage + (size_t)2 * TJ * X3_W * sizeof(double) + (size_t)TJ * 16 + (size_t)K * 16 + 16;
+    return (size_t)K * stage + (size_t)2 * TJ * X3_W * sizeof(double) + (size_t)TJ * 16 + (size_t)K * 16 + 16 + sizeof(XdSliceState) + 8;
 }
 template <int TJ, int K, int MINB, int CM>
 static cudaError_t x3_prepare(size_t *smem, int *blocks_per_sm)
@@ -1090,7 +1157,7 @@ static inline int fused3_plan_build(Fused3Plan &p, XmWork &work, int sm_count, c
     a.cbA = rm ? cbFac : cb[0]; a.cbB = cb[1]; a.cbC = cb[2]; a.cbFd = cbFd; a.cbFac = cbFac;
     a.r2 = q.p[1]; a.r1 = q.p[2]; a.undef = q.undef;
     p.batch = batch;
-    p.nblk_partials = a.ntx * a.nty * a.ntz;
+    p.nblk_partials = 2 * a.ntx * a.nty * a.ntz;       // (two sets of slots: replicated loop control alternates between them)
     const i64 tiles = (i64)a.ntx * a.nty * a.ntz * batch;
     int blocks_per_sm = 0;
 #define X3_PREP(TJ_, K_, MB_, AR_) e = x3_prepare<TJ_, K_, MB_, AR_>(&p.smem, &blocks_per_sm)
@@ -1138,7 +1205,9 @@ static inline int fused3_sweep(Fused3Plan &p, cudaStream_t stream, XdSliceState 
         a.gbar_base = p.gbar_base;
         X3_DISPATCH(p.variant, p.cm(), X3_GO);
         if (e == cudaSuccess) {
-            p.gbar_base += (unsigned long long)p.grid * (unsigned long long)(npass - 1);
+            // arrivals per CTA and launch: one per pass boundary, one more behind the last pass when the loop control is replicated
+            const bool repl = (i64)a.ntx * a.nty * a.ntz * a.batch <= (i64)p.grid;
+            p.gbar_base += (unsigned long long)p.grid * (unsigned long long)(repl ? npass : npass - 1);
             *launches += 1;
             return 0;
         }
